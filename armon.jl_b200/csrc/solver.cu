@@ -1,0 +1,644 @@
+// solver.cu -- the fused solver object behind `solver_cycle` / `next_time_step` / `next_cycle!` / `time_loop`
+// (src/solver.jl:288-403, src/reductions.jl:164-199, src/solver_state.jl:58-166) for ArmonParameters{T,<:B200Device}.
+//
+// Per cycle the stream receives: [halo exchange ->] one marching sweep kernel per axis of the splitting
+// (sweep_kernel.cuh), [NCCL all-reduce(max) of the two CFL accumulators ->] one single-thread kernel that performs
+// next_cycle! and the next cycle's time-step update on the device.  Nothing synchronises with the host: dt, time,
+// cycle count and the stop condition live in DeviceTimeState.
+#include "sweep_dispatch.h"
+
+#include <cmath>
+#include <vector>
+
+namespace {
+
+constexpr int TPB = 256;
+
+// ---- device-side time step state machine ----------------------------------------------------------------------
+__global__ void k_ts_reset(DeviceTimeState *ts, int cst_dt, double Dt)
+{
+    // reset!(global_dt), src/solver_state.jl:58-67
+    ts->cycle = 0;
+    ts->time = 0.0;
+    ts->current_dt = cst_dt ? Dt : 0.0;
+    ts->next_cycle_dt = __longlong_as_double(0x7FF0000000000000LL);
+    ts->error = 0;
+    ts->done = 0;
+    ts->acc[0][0] = ts->acc[0][1] = ts->acc[1][0] = ts->acc[1][1] = 0ULL;
+}
+
+struct CycleStepArgs {
+    int first;            // 1: called before cycle 0 (no next_cycle! to apply)
+    int acc_is_xy;        // 1: acc[0] = (x, y); 0: acc[0] = (y, x)
+    double dx, dy;        // GLOBAL cell sizes, src/reductions.jl:91-94
+    double cfl, maxtime;
+    long long maxcycle;
+    int cst_dt;
+    double Dt;
+};
+
+// next_cycle! (src/solver_state.jl:145-166) of the cycle that just ran, the loop condition of time_loop
+// (src/solver.jl:333), then next_time_step + update_dt! (src/reductions.jl:164-199, src/solver_state.jl:102-142) of the
+// cycle about to run.  SURVEY.md section 3.3 gives the recurrence this reproduces.
+__global__ void k_cycle_step(DeviceTimeState *ts, CycleStepArgs a)
+{
+    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    const unsigned long long bx = ts->acc[0][a.acc_is_xy ? 0 : 1];
+    const unsigned long long by = ts->acc[0][a.acc_is_xy ? 1 : 0];
+    ts->acc[0][0] = ts->acc[0][1] = ts->acc[1][0] = ts->acc[1][1] = 0ULL;
+    if (ts->done) return;
+
+    if (!a.first) {
+        ts->cycle += 1;
+        ts->time = __dadd_rn(ts->time, ts->current_dt);
+        if (a.cst_dt) {
+            ts->current_dt = ts->next_cycle_dt = a.Dt;
+        } else {
+            ts->current_dt = ts->next_cycle_dt;
+            ts->next_cycle_dt = inf;
+        }
+    }
+    if (!(ts->time < a.maxtime && ts->cycle < a.maxcycle)) {
+        ts->done = 1;
+        return;
+    }
+    if (a.cst_dt) {   // src/reductions.jl:165-167
+        ts->current_dt = a.Dt;
+        ts->next_cycle_dt = a.Dt;
+        return;
+    }
+    // local_time_step: min over cells of min(dx/max(|u+c|,|u-c|), dy/...) == min(dx/max_cells(|u|+c), dy/...)
+    // (division by a positive number is monotone, so the min commutes with the correctly rounded quotient)
+    const double ax = __longlong_as_double((long long)bx), ay = __longlong_as_double((long long)by);
+    double new_dt = fmin(__ddiv_rn(a.dx, ax), __ddiv_rn(a.dy, ay));
+    if (ax != ax || ay != ay) new_dt = ax + ay;   // NaN in the fields: propagate
+    const double previous_dt = ts->current_dt;
+    if (!isfinite(new_dt) || new_dt <= 0.0) {   // src/solver_state.jl:123-124
+        ts->error = ARMON_ERR_TIME;
+        ts->done = 1;
+        return;
+    } else if (previous_dt == 0.0) {
+        new_dt = __dmul_rn(a.cfl, new_dt);
+    } else {
+        new_dt = fmin(__dmul_rn(a.cfl, new_dt), __dmul_rn(1.05, previous_dt));
+    }
+    ts->next_cycle_dt = new_dt;
+    if (ts->current_dt == 0.0) ts->current_dt = new_dt;
+}
+
+// EOS_init + the first local_time_step (src/solver.jl:291-297): CFL maxima of the initial state.
+// Works on either layout: the reduction does not care about cell order.
+template <int EOS>
+__global__ void k_init_dt(long long n_rows, long long n_cols, long long pitch, int g, const double *rho,
+                          const double *u, const double *v, const double *E, double gamma, DeviceTimeState *ts)
+{
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r = blockIdx.y;
+    unsigned long long bx = 0ULL, by = 0ULL;
+    if (col < n_cols && r < n_rows) {
+        const long long i = (r + g) * pitch + (col + g);
+        sd p, c, gg;
+        if (EOS == ARMON_EOS_BIZARRIUM) eos_bizarrium<sd, false>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, gg);
+        else eos_perfect_gas<sd>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c);
+        bx = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(u[i]), c.v));
+        by = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(v[i]), c.v));
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long ox = __shfl_xor_sync(0xffffffffu, bx, off);
+        const unsigned long long oy = __shfl_xor_sync(0xffffffffu, by, off);
+        bx = ox > bx ? ox : bx;
+        by = oy > by ? oy : by;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&ts->acc[0][0], bx);
+        atomicMax(&ts->acc[0][1], by);
+    }
+}
+
+// ---- layout helpers ---------------------------------------------------------------------------------------------
+struct Ptr4 { const double *in[4]; double *out[4]; };
+
+// out[c][r] = in[r][c] for 4 arrays at once; rows x cols are the full array extents including ghosts
+__global__ void k_transpose4(Ptr4 P, long long rows, long long cols)
+{
+    __shared__ double tile[4][32][33];
+    const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        for (int j = ty; j < 32; j += 8) {
+            const long long r = r0 + j, c = c0 + tx;
+            if (r < rows && c < cols) tile[k][j][tx] = P.in[k][r * cols + c];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        for (int j = ty; j < 32; j += 8) {
+            const long long c = c0 + j, r = r0 + tx;
+            if (r < rows && c < cols) P.out[k][c * rows + r] = tile[k][tx][j];
+        }
+}
+
+// Stale p, c, g of the reference (EOS of the state at the start of the last sweep), canonical layout out.
+template <int EOS>
+__global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, const double *rho, const double *u,
+                          const double *v, const double *E, double gamma, double *p, double *c, double *gg)
+{
+    const long long ix = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 0-based real cell
+    const long long iy = blockIdx.y;
+    if (ix >= nx) return;
+    const long long io = (iy + g) * (nx + 2 * g) + (ix + g);
+    const long long ii = in_transposed ? (ix + g) * (ny + 2 * g) + (iy + g) : io;
+    sd pp, cc, g_;
+    if (EOS == ARMON_EOS_BIZARRIUM) {
+        eos_bizarrium<sd, true>(sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc, g_);
+    } else {
+        eos_perfect_gas<sd>(sd(gamma), sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc);
+        g_ = (sd(1.) + sd(gamma)) / sd(2.);
+    }
+    if (p) p[io] = pp.v;
+    if (c) c[io] = cc.v;
+    if (gg) gg[io] = g_.v;
+}
+
+bool is_pow2_double(double x)
+{
+    if (!(x > 0.0) || !std::isfinite(x)) return false;
+    int e;
+    return std::frexp(x, &e) == 0.5;
+}
+
+int split_axes(int splitting, long long cycle, int axes[3], double factors[3])
+{
+    // src/axis_splitting.jl:24-46
+    const bool even = (cycle % 2) == 0;
+    switch (splitting) {
+    case ARMON_SPLIT_SEQUENTIAL:
+        axes[0] = ARMON_AXIS_X; axes[1] = ARMON_AXIS_Y; factors[0] = factors[1] = 1.0; return 2;
+    case ARMON_SPLIT_GODUNOV:
+        axes[0] = even ? ARMON_AXIS_X : ARMON_AXIS_Y; axes[1] = even ? ARMON_AXIS_Y : ARMON_AXIS_X;
+        factors[0] = factors[1] = 1.0; return 2;
+    case ARMON_SPLIT_STRANG:
+        axes[0] = axes[2] = even ? ARMON_AXIS_X : ARMON_AXIS_Y; axes[1] = even ? ARMON_AXIS_Y : ARMON_AXIS_X;
+        factors[0] = factors[2] = 0.5; factors[1] = 1.0; return 3;
+    case ARMON_SPLIT_X_ONLY: axes[0] = ARMON_AXIS_X; factors[0] = 1.0; return 1;
+    default:                 axes[0] = ARMON_AXIS_Y; factors[0] = 1.0; return 1;
+    }
+}
+
+}   // namespace
+
+struct armon_solver {
+    armon_ctx        *ctx = nullptr;
+    armon_solver_desc d{};
+    double           *buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    double           *pcg[3] = {nullptr, nullptr, nullptr};
+    bool              bound = false;
+    int               cur = 0;                 // buffer set holding the current state (0 = main_vars, 1 = work_vars)
+    bool              cur_transposed = false;  // false: canonical rows = y; true: rows = x
+    bool              have_prev = false;       // the other set still holds the state at the start of the last sweep
+    bool              prev_transposed = false;
+    DeviceTimeState  *ts = nullptr;
+    long long         host_cycle = 0;          // cycles enqueued since the last reset
+    bool              started = false;         // initial time step enqueued
+    cudaEvent_t       ev_start = nullptr, ev_stop = nullptr;
+    bool              timed = false;
+    uint64_t          sweep_launches = 0;
+    sweep_fn_t        kernel = nullptr;
+};
+
+namespace {
+
+int solver_check(armon_solver *s, bool need_bound = true)
+{
+    ARMON_CHECK_ARG(s != nullptr && s->ctx != nullptr, "null solver");
+    if (need_bound) ARMON_CHECK_ARG(s->bound, "armon_solver_bind was not called");
+    return armon_ctx_activate(s->ctx);
+}
+
+long long n_elems(const armon_solver *s)
+{
+    return (s->d.dims.nx + 2 * s->d.dims.g) * (s->d.dims.ny + 2 * s->d.dims.g);
+}
+
+// Transpose the current state into the other buffer set.
+int transpose_current(armon_solver *s)
+{
+    const armon_dims &D = s->d.dims;
+    const long long rows = s->cur_transposed ? D.nx + 2 * D.g : D.ny + 2 * D.g;
+    const long long cols = s->cur_transposed ? D.ny + 2 * D.g : D.nx + 2 * D.g;
+    Ptr4 P;
+    for (int k = 0; k < 4; k++) { P.in[k] = s->buf[s->cur][k]; P.out[k] = s->buf[1 - s->cur][k]; }
+    const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), 1), block(32, 8, 1);
+    k_transpose4<<<grid, block, 0, s->ctx->stream>>>(P, rows, cols);
+    ARMON_LAUNCH_CHECK(s->ctx);
+    s->cur = 1 - s->cur;
+    s->cur_transposed = !s->cur_transposed;
+    s->have_prev = false;
+    return ARMON_OK;
+}
+
+// A sweep along `axis` marches along the strided dimension: X needs the transposed layout, Y the canonical one.
+int ensure_layout(armon_solver *s, int axis)
+{
+    const bool need_transposed = (axis == ARMON_AXIS_X);
+    if (need_transposed != s->cur_transposed) return transpose_current(s);
+    return ARMON_OK;
+}
+
+// block_ghost_exchange with RemoteTaskBlocks (src/halo_exchange.jl:286-354): the two sides along `axis`.  In the
+// marching layout both sides are `g` contiguous rows of each array, so there is no pack/unpack kernel: the g
+// innermost real rows are sent, the g ghost rows received (translation, same orientation as the reference's
+// pack_to_array!/unpack_from_array!, src/halo_exchange.jl:187-216).  Only rho, u, v, E travel: p, c, g are
+// recomputed by the receiver from the same values, bit for bit.
+int halo_exchange(armon_solver *s, int axis)
+{
+    const armon_dims &D = s->d.dims;
+    const int lo_side = axis == ARMON_AXIS_X ? ARMON_SIDE_LEFT : ARMON_SIDE_BOTTOM;
+    const int lo = s->d.neighbours[lo_side], hi = s->d.neighbours[lo_side + 1];
+    if (lo < 0 && hi < 0) return ARMON_OK;
+    if (!s->ctx->comm) {
+        armon_set_error("a neighbour rank is set but the context has no communicator (armon_ctx_comm_init)");
+        return ARMON_ERR_INVALID;
+    }
+    const long long nm = axis == ARMON_AXIS_X ? D.nx : D.ny;
+    const long long pitch = (axis == ARMON_AXIS_X ? D.ny : D.nx) + 2 * D.g;
+    const size_t count = (size_t)(D.g * pitch);
+    ARMON_NCCL(ncclGroupStart());
+    for (int k = 0; k < 4; k++) {
+        double *a = s->buf[s->cur][k];
+        if (lo >= 0) {
+            ARMON_NCCL(ncclSend(a + D.g * pitch, count, ncclDouble, lo, s->ctx->comm, s->ctx->stream));
+            ARMON_NCCL(ncclRecv(a, count, ncclDouble, lo, s->ctx->comm, s->ctx->stream));
+        }
+        if (hi >= 0) {
+            ARMON_NCCL(ncclSend(a + nm * pitch, count, ncclDouble, hi, s->ctx->comm, s->ctx->stream));
+            ARMON_NCCL(ncclRecv(a + (nm + D.g) * pitch, count, ncclDouble, hi, s->ctx->comm, s->ctx->stream));
+        }
+    }
+    ARMON_NCCL(ncclGroupEnd());
+    return ARMON_OK;
+}
+
+int pick_segment(const armon_solver *s, long long nm, long long nw)
+{
+    if (s->d.march_segment > 0) {
+        int seg = (s->d.march_segment + SWEEP_CHUNK - 1) / SWEEP_CHUNK * SWEEP_CHUNK;
+        return seg;
+    }
+    // as long as possible (8 warm-up rows per segment are redundant work) while keeping >= 6 waves of CTAs
+    const long long ncol = (nw + SWEEP_TPB - 1) / SWEEP_TPB;
+    const long long want = 6LL * 2 * s->ctx->sm_count;
+    const int cands[] = {512, 256, 128, 64, 32, 16};
+    for (int seg : cands) {
+        if (seg > nm && seg != 16) continue;
+        if (ncol * ((nm + seg - 1) / seg) >= want) return seg;
+    }
+    return nm >= 64 ? 32 : 16;
+}
+
+int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle, int next_axis)
+{
+    if (int rc = ensure_layout(s, axis)) return rc;
+    if (int rc = halo_exchange(s, axis)) return rc;
+
+    const armon_dims &D = s->d.dims;
+    const armon_test_case &tc = s->d.tc;
+    const bool x = axis == ARMON_AXIS_X;
+    SweepArgs A;
+    const int in_set = s->cur, out_set = 1 - s->cur;
+    // roles: (rho, ua, ut, E); storage order of a set: (rho, u, v, E)
+    const int role[4] = {0, x ? 1 : 2, x ? 2 : 1, 3};
+    for (int k = 0; k < 4; k++) { A.in[k] = s->buf[in_set][role[k]]; A.out[k] = s->buf[out_set][role[k]]; }
+    A.nm = x ? D.nx : D.ny;
+    A.nw = x ? D.ny : D.nx;
+    A.g = (int)D.g;
+    A.pitch_in = A.nw + 2 * D.g;
+    A.transpose_out = (next_axis != axis) ? 1 : 0;
+    A.pitch_out = A.transpose_out ? A.nm + 2 * D.g : A.nw + 2 * D.g;
+    A.seg = pick_segment(s, A.nm, A.nw);
+    const int lo_side = x ? ARMON_SIDE_LEFT : ARMON_SIDE_BOTTOM, hi_side = lo_side + 1;
+    A.mirror_lo = s->d.neighbours[lo_side] < 0;
+    A.mirror_hi = s->d.neighbours[hi_side] < 0;
+    A.bc_a_lo = x ? tc.bc_u[lo_side] : tc.bc_v[lo_side];
+    A.bc_t_lo = x ? tc.bc_v[lo_side] : tc.bc_u[lo_side];
+    A.bc_a_hi = x ? tc.bc_u[hi_side] : tc.bc_v[hi_side];
+    A.bc_t_hi = x ? tc.bc_v[hi_side] : tc.bc_u[hi_side];
+    A.dx = s->d.domain_size[axis] / (double)(x ? s->d.global_nx : s->d.global_ny);   // update_solver_state!
+    A.dx_pow2 = is_pow2_double(A.dx) ? 1 : 0;
+    A.inv_dx = 1.0 / A.dx;
+    A.dt_factor = dt_factor;
+    A.gamma = tc.gamma;
+    A.ts = s->ts;
+    A.acc_slot = last_of_cycle ? 0 : 1;
+
+    const dim3 grid((unsigned)((A.nw + SWEEP_TPB - 1) / SWEEP_TPB), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
+    s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
+    ARMON_LAUNCH_CHECK(s->ctx);
+    s->sweep_launches++;
+
+    s->have_prev = true;
+    s->prev_transposed = s->cur_transposed;
+    s->cur = out_set;
+    if (A.transpose_out) s->cur_transposed = !s->cur_transposed;
+    return ARMON_OK;
+}
+
+int allreduce_acc(armon_solver *s)
+{
+    if (s->ctx->comm && s->ctx->nranks > 1) {
+        // MPI_Iallreduce(MIN) of the local dt (src/utils.jl:126-134, src/solver_state.jl:107-111) becomes an
+        // all-reduce(max) of the two CFL maxima: the min of the quotients is the quotient of the max.
+        ARMON_NCCL(ncclAllReduce(&s->ts->acc[0][0], &s->ts->acc[0][0], 2, ncclUint64, ncclMax, s->ctx->comm,
+                                 s->ctx->stream));
+    }
+    return ARMON_OK;
+}
+
+int launch_cycle_step(armon_solver *s, bool first, bool acc_is_xy)
+{
+    CycleStepArgs a;
+    a.first = first ? 1 : 0;
+    a.acc_is_xy = acc_is_xy ? 1 : 0;
+    a.dx = s->d.domain_size[0] / (double)s->d.global_nx;
+    a.dy = s->d.domain_size[1] / (double)s->d.global_ny;
+    a.cfl = s->d.cfl;
+    a.maxtime = s->d.maxtime;
+    a.maxcycle = s->d.maxcycle;
+    a.cst_dt = s->d.cst_dt;
+    a.Dt = s->d.Dt;
+    k_cycle_step<<<1, 1, 0, s->ctx->stream>>>(s->ts, a);
+    ARMON_LAUNCH_CHECK(s->ctx);
+    return ARMON_OK;
+}
+
+int launch_init_dt(armon_solver *s)
+{
+    const armon_dims &D = s->d.dims;
+    const long long n_rows = s->cur_transposed ? D.nx : D.ny, n_cols = s->cur_transposed ? D.ny : D.nx;
+    const long long pitch = n_cols + 2 * D.g;
+    double *const *b = s->buf[s->cur];
+    const dim3 grid((unsigned)((n_cols + TPB - 1) / TPB), (unsigned)n_rows, 1);
+    if (s->d.tc.eos == ARMON_EOS_BIZARRIUM)
+        k_init_dt<ARMON_EOS_BIZARRIUM><<<grid, TPB, 0, s->ctx->stream>>>(n_rows, n_cols, pitch, (int)D.g, b[0], b[1],
+                                                                         b[2], b[3], s->d.tc.gamma, s->ts);
+    else
+        k_init_dt<ARMON_EOS_PERFECT_GAS><<<grid, TPB, 0, s->ctx->stream>>>(n_rows, n_cols, pitch, (int)D.g, b[0], b[1],
+                                                                           b[2], b[3], s->d.tc.gamma, s->ts);
+    ARMON_LAUNCH_CHECK(s->ctx);
+    return ARMON_OK;
+}
+
+int enqueue_cycle(armon_solver *s)
+{
+    if (!s->started) {
+        // cycle 0: EOS_init + first time step (src/solver.jl:291-297)
+        if (int rc = launch_init_dt(s)) return rc;
+        if (int rc = allreduce_acc(s)) return rc;
+        if (int rc = launch_cycle_step(s, true, true)) return rc;
+        s->started = true;
+    }
+    int axes[3], next_axes[3];
+    double factors[3], next_factors[3];
+    const int n = split_axes(s->d.splitting, s->host_cycle, axes, factors);
+    split_axes(s->d.splitting, s->host_cycle + 1, next_axes, next_factors);
+    for (int k = 0; k < n; k++) {
+        const bool last = k == n - 1;
+        const int next_axis = last ? next_axes[0] : axes[k + 1];
+        if (int rc = launch_sweep(s, axes[k], factors[k], last, next_axis)) return rc;
+    }
+    if (int rc = allreduce_acc(s)) return rc;
+    // the last sweep ran along axes[n-1]: acc[0] = (march axis, transverse axis)
+    if (int rc = launch_cycle_step(s, false, axes[n - 1] == ARMON_AXIS_X)) return rc;
+    s->host_cycle++;
+    return ARMON_OK;
+}
+
+int read_state(armon_solver *s, armon_time_state *out)
+{
+    DeviceTimeState *h = reinterpret_cast<DeviceTimeState *>(s->ctx->pinned);
+    ARMON_CUDA(cudaMemcpyAsync(h, s->ts, sizeof(DeviceTimeState), cudaMemcpyDeviceToHost, s->ctx->stream));
+    ARMON_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    out->cycle = h->cycle;
+    out->time = h->time;
+    out->current_dt = h->current_dt;
+    out->next_cycle_dt = h->next_cycle_dt;
+    out->error = h->error;
+    out->done = h->done;
+    return ARMON_OK;
+}
+
+}   // namespace
+
+extern "C" {
+
+int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_solver **out)
+{
+    ARMON_CHECK_ARG(ctx && desc && out, "null argument");
+    *out = nullptr;
+    if (int rc = armon_ctx_activate(ctx)) return rc;
+    const armon_dims &D = desc->dims;
+    ARMON_CHECK_ARG(D.nx > 0 && D.ny > 0, "empty sub-domain");
+    ARMON_CHECK_ARG(D.g == 4, "the fused sweep needs nghost == 4 (dependency cone of GAD + euler_2nd, SURVEY.md 8a)");
+    ARMON_CHECK_ARG(D.nx >= D.g && D.ny >= D.g, "sub-domain smaller than the ghost width (src/parameters.jl:684-690)");
+    ARMON_CHECK_ARG(desc->riemann == ARMON_RIEMANN_GODUNOV || desc->riemann == ARMON_RIEMANN_GAD, "riemann scheme");
+    ARMON_CHECK_ARG(desc->limiter >= 0 && desc->limiter <= 2, "limiter");
+    ARMON_CHECK_ARG(desc->projection == ARMON_PROJ_EULER || desc->projection == ARMON_PROJ_EULER_2ND, "projection");
+    ARMON_CHECK_ARG(desc->splitting >= 0 && desc->splitting <= 4, "axis splitting");
+    ARMON_CHECK_ARG(desc->tc.eos == ARMON_EOS_PERFECT_GAS || desc->tc.eos == ARMON_EOS_BIZARRIUM, "EOS");
+    ARMON_CHECK_ARG(desc->math_mode == ARMON_MATH_STRICT || desc->math_mode == ARMON_MATH_FAST, "math mode");
+    ARMON_CHECK_ARG(!desc->cst_dt || desc->Dt != 0.0, "Dt == 0 with constant step enabled");
+
+    armon_solver *s = new armon_solver();
+    s->ctx = ctx;
+    s->d = *desc;
+    const int rl = desc->riemann == ARMON_RIEMANN_GODUNOV ? 0 : 1 + desc->limiter;
+    const bool biz = desc->tc.eos == ARMON_EOS_BIZARRIUM;
+    if (desc->math_mode == ARMON_MATH_STRICT)
+        s->kernel = biz ? sweep_table_strict_biz(rl, desc->projection) : sweep_table_strict_pg(rl, desc->projection);
+    else
+        s->kernel = biz ? sweep_table_fast_biz(rl, desc->projection) : sweep_table_fast_pg(rl, desc->projection);
+    if (!s->kernel) {
+        delete s;
+        armon_set_error("no sweep kernel for this scheme combination");
+        return ARMON_ERR_INVALID;
+    }
+    ARMON_CUDA(cudaMalloc(&s->ts, sizeof(DeviceTimeState)));
+    ARMON_CUDA(cudaEventCreate(&s->ev_start));
+    ARMON_CUDA(cudaEventCreate(&s->ev_stop));
+    k_ts_reset<<<1, 1, 0, ctx->stream>>>(s->ts, desc->cst_dt, desc->Dt);
+    ARMON_LAUNCH_CHECK(ctx);
+    *out = s;
+    return ARMON_OK;
+}
+
+int armon_solver_destroy(armon_solver *s)
+{
+    if (!s) return ARMON_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->ts) cudaFree(s->ts);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    delete s;
+    return ARMON_OK;
+}
+
+int armon_solver_bind(armon_solver *s, double *const main_vars[4], double *const work_vars[4], double *const pcg[3])
+{
+    if (int rc = solver_check(s, false)) return rc;
+    ARMON_CHECK_ARG(main_vars && work_vars, "null array lists");
+    for (int k = 0; k < 4; k++) {
+        ARMON_CHECK_ARG(main_vars[k] && work_vars[k], "null device array");
+        s->buf[0][k] = main_vars[k];
+        s->buf[1][k] = work_vars[k];
+    }
+    for (int k = 0; k < 3; k++) s->pcg[k] = pcg ? pcg[k] : nullptr;
+    s->bound = true;
+    s->cur = 0;
+    s->cur_transposed = false;
+    s->have_prev = false;
+    return ARMON_OK;
+}
+
+int armon_solver_reset(armon_solver *s)
+{
+    if (int rc = solver_check(s)) return rc;
+    k_ts_reset<<<1, 1, 0, s->ctx->stream>>>(s->ts, s->d.cst_dt, s->d.Dt);
+    ARMON_LAUNCH_CHECK(s->ctx);
+    s->host_cycle = 0;
+    s->started = false;
+    s->cur = 0;
+    s->cur_transposed = false;
+    s->have_prev = false;
+    s->timed = false;
+    return ARMON_OK;
+}
+
+int armon_solver_init(armon_solver *s)
+{
+    if (int rc = solver_check(s)) return rc;
+    const armon_solver_desc &d = s->d;
+    if (int rc = armon_init_test(s->ctx, d.dims, d.origin_ix, d.origin_iy, d.global_nx, d.global_ny, d.domain_size,
+                                 d.origin, &d.tc, nullptr, nullptr, nullptr, s->buf[0][0], s->buf[0][3], s->buf[0][1],
+                                 s->buf[0][2], s->pcg[0], s->pcg[1], s->pcg[2], nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr))
+        return rc;
+    return armon_solver_reset(s);
+}
+
+int armon_solver_run(armon_solver *s, int64_t n_cycles)
+{
+    if (int rc = solver_check(s)) return rc;
+    ARMON_CHECK_ARG(n_cycles >= 0, "negative cycle count");
+    ARMON_CUDA(cudaEventRecord(s->ev_start, s->ctx->stream));
+    for (int64_t c = 0; c < n_cycles; c++)
+        if (int rc = enqueue_cycle(s)) return rc;
+    ARMON_CUDA(cudaEventRecord(s->ev_stop, s->ctx->stream));
+    s->timed = true;
+    return ARMON_OK;
+}
+
+int armon_solver_state(armon_solver *s, armon_time_state *out)
+{
+    if (int rc = solver_check(s, false)) return rc;
+    ARMON_CHECK_ARG(out != nullptr, "null state");
+    return read_state(s, out);
+}
+
+int armon_solver_time_loop(armon_solver *s)
+{
+    if (int rc = solver_check(s)) return rc;
+    ARMON_CUDA(cudaEventRecord(s->ev_start, s->ctx->stream));
+    armon_time_state st;
+    if (s->d.maxcycle <= 0 || !(0.0 < s->d.maxtime)) {   // `while time < maxtime && cycle < maxcycle` never entered
+        ARMON_CUDA(cudaEventRecord(s->ev_stop, s->ctx->stream));
+        s->timed = true;
+        return ARMON_OK;
+    }
+    if (int rc = enqueue_cycle(s)) return rc;
+    for (;;) {
+        if (int rc = read_state(s, &st)) return rc;
+        if (st.error) {
+            armon_set_error("Invalid time step for cycle %lld", (long long)st.cycle);
+            return ARMON_ERR_TIME;
+        }
+        if (st.done) break;
+        // Lower bound of the cycles still to run: the time step grows by at most 5% per cycle
+        // (src/solver_state.jl:127-130), so n cycles advance the time by at most dt*(1.05^n - 1)/0.05.
+        long long batch = 1;
+        const double remaining = s->d.maxtime - st.time;
+        if (st.current_dt > 0.0 && remaining > 0.0) {
+            const double n = s->d.cst_dt ? remaining / st.current_dt
+                                         : std::log1p(0.05 * remaining / st.current_dt) / std::log(1.05);
+            batch = (long long)std::floor(n) - 1;
+        }
+        const long long left = s->d.maxcycle - st.cycle;
+        if (batch > left) batch = left;
+        if (batch > 4096) batch = 4096;
+        if (batch < 1) batch = 1;
+        for (long long c = 0; c < batch; c++)
+            if (int rc = enqueue_cycle(s)) return rc;
+    }
+    ARMON_CUDA(cudaEventRecord(s->ev_stop, s->ctx->stream));
+    s->timed = true;
+    return ARMON_OK;
+}
+
+int armon_solver_finalize(armon_solver *s)
+{
+    if (int rc = solver_check(s)) return rc;
+    const armon_dims &D = s->d.dims;
+    // 1. stale p, c, g from the state at the start of the last sweep (still intact in the other buffer set)
+    if (s->have_prev && (s->pcg[0] || s->pcg[1] || s->pcg[2])) {
+        double *const *b = s->buf[1 - s->cur];
+        const dim3 grid((unsigned)((D.nx + TPB - 1) / TPB), (unsigned)D.ny, 1);
+        if (s->d.tc.eos == ARMON_EOS_BIZARRIUM)
+            k_eos_pcg<ARMON_EOS_BIZARRIUM><<<grid, TPB, 0, s->ctx->stream>>>(
+                D.nx, D.ny, (int)D.g, s->prev_transposed, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1], s->pcg[2]);
+        else
+            k_eos_pcg<ARMON_EOS_PERFECT_GAS><<<grid, TPB, 0, s->ctx->stream>>>(
+                D.nx, D.ny, (int)D.g, s->prev_transposed, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1], s->pcg[2]);
+        ARMON_LAUNCH_CHECK(s->ctx);
+    }
+    s->have_prev = false;
+    // 2. canonical layout, in main_vars
+    if (s->cur_transposed) {
+        if (int rc = transpose_current(s)) return rc;
+    }
+    if (s->cur != 0) {
+        for (int k = 0; k < 4; k++)
+            ARMON_CUDA(cudaMemcpyAsync(s->buf[0][k], s->buf[1][k], (size_t)n_elems(s) * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, s->ctx->stream));
+        s->cur = 0;
+    }
+    return ARMON_OK;
+}
+
+int armon_solver_halo_exchange(armon_solver *s, int axis)
+{
+    if (int rc = solver_check(s)) return rc;
+    ARMON_CHECK_ARG(axis == ARMON_AXIS_X || axis == ARMON_AXIS_Y, "axis");
+    if (int rc = ensure_layout(s, axis)) return rc;
+    return halo_exchange(s, axis);
+}
+
+int armon_solver_elapsed_ms(armon_solver *s, float *ms)
+{
+    if (int rc = solver_check(s, false)) return rc;
+    ARMON_CHECK_ARG(ms != nullptr, "null result");
+    ARMON_CHECK_ARG(s->timed, "no armon_solver_run / armon_solver_time_loop call to time");
+    ARMON_CUDA(cudaEventSynchronize(s->ev_stop));
+    ARMON_CUDA(cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
+    return ARMON_OK;
+}
+
+int armon_solver_sweep_launches(armon_solver *s, uint64_t *count)
+{
+    if (int rc = solver_check(s, false)) return rc;
+    ARMON_CHECK_ARG(count != nullptr, "null result");
+    *count = s->sweep_launches;
+    return ARMON_OK;
+}
+
+}   // extern "C"

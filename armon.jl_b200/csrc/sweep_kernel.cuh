@@ -1,0 +1,369 @@
+// sweep_kernel.cuh -- the fused axis-sweep "marching" kernel (the product's hot path).
+//
+// One launch replaces, for one axis sweep of solver_cycle (src/solver.jl:300-317):
+//   update_EOS!            (src/kernels.jl:4-55)
+//   boundary_conditions!   (src/halo_exchange.jl:2-36)      -- by mirrored indexing at global edges
+//   numerical_fluxes!      (src/riemann_schemes.jl:21-123)  -- acoustic / acoustic_GAD + limiter
+//   cell_update!           (src/kernels.jl:58-68)
+//   advection_fluxes!      (src/projection_schemes.jl:62-124)
+//   euler_projection!      (src/projection_schemes.jl:23-41)
+// and accumulates the maxima needed by the next cycle's dtCFL reduction (src/reductions.jl:2-20).
+//
+// Data layout.  Arrays are [march axis][contiguous axis] including g ghosts on every side: the swept axis is always
+// the strided one.  The canonical BlockData layout (rows = y) is therefore the right input for a Y sweep; an X
+// sweep reads the transposed layout.  A sweep writes its result either in the layout it read or transposed
+// (`transpose_out`), so that alternating X/Y sweeps never need a separate transposition pass.
+//
+// Parallelisation.  thread <-> one column of the contiguous axis (coalesced 8-byte loads, 256 B per warp and
+// array row); blockIdx.y <-> a segment of `seg` cells of the march axis.  Each thread marches along its column
+// keeping the whole 9-cell dependency cone in a rolling register window: at the step that
+// loads cell a it evaluates EOS(a), the Godunov interface a, the GAD flux a-1, the Lagrangian cell a-2, the
+// advection flux a-3 and projects cell a-4.  Every input is read once (plus 8 warm-up rows per segment), every
+// interface/cell quantity is computed once, nothing intermediate touches memory: 64 B of HBM traffic per cell.
+// Inputs are prefetched 4 rows ahead (16 independent 8-byte loads in flight per thread).
+//
+// The expression order of the reference source is kept; with R = sd every operation is an
+// explicitly rounded IEEE operation and the result is bit-identical to the strict CPU oracle.  Only rewrites that
+// are exact in IEEE arithmetic are applied: x/2 -> x*0.5, x/dx -> x*(1/dx) when dx is a power of two,
+// s*x with s = sign(..) in {-1,0,1} -> sign-bit flips, max(|u+c|,|u-c|) -> |u|+c for c >= 0.
+#pragma once
+
+#include "common.cuh"
+
+constexpr int SWEEP_TPB = 128;      // threads per CTA = columns per CTA
+constexpr int SWEEP_CHUNK = 8;      // outputs between two flushes of the transposed staging buffer
+constexpr int SWEEP_STAGE_PITCH = SWEEP_CHUNK + 1;   // odd pitch: conflict-free 64-bit shared-memory writes
+
+struct SweepArgs {
+    const double *in[4];    // rho, ua, ut, E (ua: velocity along the march axis, ut: transverse velocity)
+    double       *out[4];
+    long long nm, nw;       // real cells along the march axis / along the contiguous axis
+    long long pitch_in;     // nw + 2g
+    long long pitch_out;    // transposed output: nm + 2g, else nw + 2g
+    int g;
+    int seg;                // outputs per march segment, multiple of SWEEP_CHUNK
+    int transpose_out;
+    int mirror_lo, mirror_hi;   // 1: global edge, boundary condition by mirroring; 0: ghost rows hold the neighbour's cells
+    double bc_a_lo, bc_t_lo, bc_a_hi, bc_t_hi;   // velocity factors of boundary_condition(test, side)
+    double dx, inv_dx;      // cell size along the march axis
+    int dx_pow2;            // inv_dx is exact: x/dx == x*inv_dx bit for bit
+    double dt_factor;       // axis-splitting factor (src/axis_splitting.jl:24-46)
+    double gamma;
+    DeviceTimeState *ts;
+    int acc_slot;
+};
+
+// exact s*x for s = sign(src) in {-1, +1}: flip the sign bit of x when src is negative
+__device__ __forceinline__ double flip_sign_by(double x, double src)
+{
+    const unsigned long long sb = (unsigned long long)__double_as_longlong(src) & 0x8000000000000000ULL;
+    return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(x) ^ sb));
+}
+
+// src/projection_schemes.jl:15-20, with the multiplications by s = sign(d_p) done on the sign bit (exact)
+template <class R> __device__ __forceinline__ R slope_minmod_fused(R qm, R q0, R qp, R r_m, R r_p)
+{
+    const R d_p = r_p * (qp - q0);
+    const R d_m = r_m * (q0 - qm);
+    const double a = fabs(d_p.v);                      // s * d_p
+    const double b = flip_sign_by(d_m.v, d_p.v);       // s * d_m
+    const double m = fmax(0.0, fmin(a, b));
+    const double res = flip_sign_by(m, d_p.v);         // s * max(0, min(..))
+    return R(d_p.v == 0.0 ? 0.0 : res);
+}
+
+template <class R> __device__ __forceinline__ R div_by_dx(R x, const SweepArgs &A)
+{
+    return A.dx_pow2 ? x * R(A.inv_dx) : x / R(A.dx);
+}
+
+template <class R, int EOS> __device__ __forceinline__ void eos_eval(const SweepArgs &A, R rho, R ua, R ut, R E, R &p, R &c)
+{
+    if (EOS == ARMON_EOS_BIZARRIUM) {
+        R g;
+        eos_bizarrium<R, false>(rho, ua, ut, E, p, c, g);
+    } else {
+        eos_perfect_gas<R>(R(A.gamma), rho, ua, ut, E, p, c);
+    }
+}
+
+// Rolling window of the march, 4-slot rings indexed by (cell index mod 4) with compile-time slots.
+template <class R> struct Pipe {
+    R cu[4], cp[4], crc[4], cdm[4], cut[4], cE[4], cc[4];   // cells: ua, p, rho*c, rho*dx, ut, E, c
+    R Gu[4], Gp[4];                                         // first-order (Godunov) interface state
+    R Fu[4], Fp[4], FpFu[4];                                // flux actually used (GAD or Godunov), and p*u
+    R disp[4];                                              // dt * Fu
+    R dxl[4];                                               // Lagrangian cell width dx + dt*(Fu[k+1]-Fu[k])
+    R Lr[4], Lu[4], Lt[4], LE[4], Lru[4], Lrt[4], LrE[4];   // Lagrangian cell: rho, ua, ut, E and rho*{ua,ut,E}
+    R Ar, Aru, Art, ArE;                                    // advection flux of the previous interface
+};
+
+struct SweepThread {
+    long long col;         // element offset of this thread's column inside a row (w + g)
+    bool      valid;       // column holds a real cell
+    unsigned long long amax, tmax;   // dt accumulators (integer images of non-negative doubles)
+};
+
+__device__ __forceinline__ long long march_row(const SweepArgs &A, long long a)
+{
+    long long r = a;
+    if (a < 0 && A.mirror_lo) r = -1 - a;
+    else if (a >= A.nm && A.mirror_hi) r = 2 * A.nm - 1 - a;
+    // clamp: prefetches past the last needed row (and mirrors of a ragged last chunk) stay inside the array
+    const long long rmax = A.nm + A.g - 1, rmin = -(long long)A.g;
+    r = r > rmax ? rmax : (r < rmin ? rmin : r);
+    return r + A.g;
+}
+
+__device__ __forceinline__ void issue_loads(const SweepArgs &A, const SweepThread &T, long long a, double v[4])
+{
+    const long long idx = march_row(A, a) * A.pitch_in + T.col;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = __ldg(A.in[k] + idx);
+}
+
+// One march step: consumes cell a (already in `in`), emits cell a-4.  J = (a - a_begin) & 3 is static.
+template <class R, int RL, int PROJ, int EOS, int J, bool EMIT>
+__device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, Pipe<R> &P, double (&in)[4][4],
+                                           const long long a, const long long a_last, const R dt,
+                                           const int k_chunk, const long long m1, double *stage)
+{
+    constexpr int S0 = J & 3, S1 = (J + 3) & 3, S2 = (J + 2) & 3, S3 = (J + 1) & 3;
+    const R dx(A.dx);
+
+    // ---- cell a: boundary factors, EOS (src/kernels.jl:4-55) ----
+    R rho(in[J][0]), ua(in[J][1]), ut(in[J][2]), E(in[J][3]);
+    if (a < 0 && A.mirror_lo) { ua = ua * R(A.bc_a_lo); ut = ut * R(A.bc_t_lo); }
+    else if (a >= A.nm && A.mirror_hi) { ua = ua * R(A.bc_a_hi); ut = ut * R(A.bc_t_hi); }
+    // prefetch the cell consumed 4 steps from now into the slot just freed
+    {
+        const long long an = a + 4 > a_last ? a_last : a + 4;
+        issue_loads(A, T, an, in[J]);
+    }
+    const R c_out = P.cc[S0];   // c of cell a-4 (EOS at the start of this sweep), read before the slot is reused
+    R p, c;
+    eos_eval<R, EOS>(A, rho, ua, ut, E, p, c);
+    const R rc = rho * c;
+    P.cu[S0] = ua; P.cp[S0] = p; P.crc[S0] = rc; P.cdm[S0] = rho * dx; P.cut[S0] = ut; P.cE[S0] = E; P.cc[S0] = c;
+
+    // ---- Godunov state at interface a (cells a-1, a): src/riemann_schemes.jl:21-30 ----
+    acoustic_godunov<R>(P.crc[S1], rc, P.cu[S1], ua, P.cp[S1], p, P.Gu[S0], P.Gp[S0]);
+
+    // ---- flux at interface i = a-1 (cells a-2, a-1) ----
+    if (RL == 0) {   // acoustic!  src/riemann_schemes.jl:33-43
+        P.Fu[S1] = P.Gu[S1];
+        P.Fp[S1] = P.Gp[S1];
+    } else {         // acoustic_GAD!  src/riemann_schemes.jl:55-104
+        constexpr int LIM = RL - 1;
+        const R u_i = P.cu[S1], u_im = P.cu[S2], p_i = P.cp[S1], p_im = P.cp[S2];
+        const R us_i = P.Gu[S1], ps_i = P.Gp[S1];
+        R r_um = (P.Gu[S0] - u_i) / ((us_i - u_im) + R(1e-6));
+        R r_pm = (P.Gp[S0] - p_i) / ((ps_i - p_im) + R(1e-6));
+        R r_up = (u_im - P.Gu[S2]) / ((u_i - us_i) + R(1e-6));
+        R r_pp = (p_im - P.Gp[S2]) / ((p_i - ps_i) + R(1e-6));
+        r_um = limiter<R, LIM>(r_um);
+        r_pm = limiter<R, LIM>(r_pm);
+        r_up = limiter<R, LIM>(r_up);
+        r_pp = limiter<R, LIM>(r_pp);
+        const R Dm = (P.cdm[S2] + P.cdm[S1]) * R(0.5);                                   // (dm_l + dm_r) / 2
+        const R theta = R(0.5) * (R(1.) - ((P.crc[S2] + P.crc[S1]) * R(0.5)) * (dt / Dm));
+        P.Fu[S1] = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
+        P.Fp[S1] = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
+    }
+    P.FpFu[S1] = P.Fp[S1] * P.Fu[S1];
+    P.disp[S1] = dt * P.Fu[S1];
+
+    // ---- Lagrangian update of cell k = a-2: src/kernels.jl:58-68 ----
+    {
+        const R dxl = dx + dt * (P.Fu[S1] - P.Fu[S2]);
+        const R dm = P.cdm[S2];
+        const R dtdm = dt / dm;
+        const R Lr = dm / dxl;
+        const R Lu = P.cu[S2] + dtdm * (P.Fp[S2] - P.Fp[S1]);
+        const R LE = P.cE[S2] + dtdm * (P.FpFu[S2] - P.FpFu[S1]);
+        const R Lt = P.cut[S2];
+        P.dxl[S2] = dxl; P.Lr[S2] = Lr; P.Lu[S2] = Lu; P.LE[S2] = LE; P.Lt[S2] = Lt;
+        P.Lru[S2] = Lr * Lu; P.Lrt[S2] = Lr * Lt; P.LrE[S2] = Lr * LE;
+    }
+
+    // ---- advection flux at interface is = a-3: src/projection_schemes.jl:62-124 ----
+    // ring slots: cells a-5 -> S1, a-4 -> S0, a-3 -> S3, a-2 -> S2 ; disp(a-4) -> S0, disp(a-3) -> S3, disp(a-2) -> S2
+    R Anr, Anru, Anrt, AnrE;
+    {
+        const R d = P.disp[S3];
+        const bool pos = d.v > 0.0;
+        if (PROJ == ARMON_PROJ_EULER_2ND) {
+            const R dxe = rsel(pos, -(dx - P.disp[S0]), dx + P.disp[S2]);
+            const R dxl_m = rsel(pos, P.dxl[S1], P.dxl[S0]);
+            const R dxl_0 = rsel(pos, P.dxl[S0], P.dxl[S3]);
+            const R dxl_p = rsel(pos, P.dxl[S3], P.dxl[S2]);
+            const R two_dxl = R(2.) * dxl_0;
+            const R r_m = two_dxl / (dxl_0 + dxl_m);
+            const R r_p = two_dxl / (dxl_0 + dxl_p);
+            const R lf = dxe / two_dxl;
+#define ARMON_ADVECT(q, res)                                                                         \
+            {                                                                                        \
+                const R qm = rsel(pos, P.q[S1], P.q[S0]);                                            \
+                const R q0 = rsel(pos, P.q[S0], P.q[S3]);                                            \
+                const R qp = rsel(pos, P.q[S3], P.q[S2]);                                            \
+                res = d * (q0 - slope_minmod_fused<R>(qm, q0, qp, r_m, r_p) * lf);                   \
+            }
+            ARMON_ADVECT(Lr, Anr)
+            ARMON_ADVECT(Lru, Anru)
+            ARMON_ADVECT(Lrt, Anrt)
+            ARMON_ADVECT(LrE, AnrE)
+#undef ARMON_ADVECT
+        } else {
+            Anr = d * rsel(pos, P.Lr[S0], P.Lr[S3]);
+            Anru = d * rsel(pos, P.Lru[S0], P.Lru[S3]);
+            Anrt = d * rsel(pos, P.Lrt[S0], P.Lrt[S3]);
+            AnrE = d * rsel(pos, P.LrE[S0], P.LrE[S3]);
+        }
+    }
+
+    // ---- projection of cell k = a-4: src/projection_schemes.jl:23-41 ----
+    if (EMIT) {
+        const R dXr = P.dxl[S0] * P.Lr[S0];
+        const R t_r = div_by_dx<R>(dXr - (Anr - P.Ar), A);
+        const R t_ru = div_by_dx<R>(dXr * P.Lu[S0] - (Anru - P.Aru), A);
+        const R t_rt = div_by_dx<R>(dXr * P.Lt[S0] - (Anrt - P.Art), A);
+        const R t_rE = div_by_dx<R>(dXr * P.LE[S0] - (AnrE - P.ArE), A);
+        const R o_ua = t_ru / t_r, o_ut = t_rt / t_r, o_E = t_rE / t_r;
+        const long long m = a - 4;
+        const bool store = T.valid && m < m1;
+        // dtCFL accumulators (src/reductions.jl:14-20): max(|u+c|,|u-c|) == |u|+c, new velocities, c of this sweep's EOS
+        if (store) {
+            const unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
+            const unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+            T.amax = ba > T.amax ? ba : T.amax;
+            T.tmax = bt > T.tmax ? bt : T.tmax;
+        }
+        if (A.transpose_out) {
+            // stage[var][lane][k]: flushed as rows of SWEEP_CHUNK contiguous doubles by flush_stage()
+            double *s = stage + (threadIdx.x & 31) * SWEEP_STAGE_PITCH + k_chunk;
+            s[0 * 32 * SWEEP_STAGE_PITCH] = t_r.v;
+            s[1 * 32 * SWEEP_STAGE_PITCH] = o_ua.v;
+            s[2 * 32 * SWEEP_STAGE_PITCH] = o_ut.v;
+            s[3 * 32 * SWEEP_STAGE_PITCH] = o_E.v;
+        } else if (store) {
+            const long long o = (m + A.g) * A.pitch_out + T.col;
+            A.out[0][o] = t_r.v;
+            A.out[1][o] = o_ua.v;
+            A.out[2][o] = o_ut.v;
+            A.out[3][o] = o_E.v;
+        }
+    }
+    P.Ar = Anr; P.Aru = Anru; P.Art = Anrt; P.ArE = AnrE;
+}
+
+// Transposed store of one chunk: the warp's staging buffer holds, per variable, 32 columns x SWEEP_CHUNK march
+// cells; each column becomes a row of the transposed array, written as SWEEP_CHUNK contiguous doubles (4 rows
+// per warp store instruction).
+__device__ __forceinline__ void flush_stage(const SweepArgs &A, const double *stage, long long w0, long long mb, long long m1)
+{
+    const int lane = threadIdx.x & 31;
+    const int rsub = lane / SWEEP_CHUNK, col = lane % SWEEP_CHUNK;
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+#pragma unroll
+        for (int it = 0; it < 32 / (32 / SWEEP_CHUNK); it++) {
+            const int r = it * (32 / SWEEP_CHUNK) + rsub;
+            const double val = stage[(v * 32 + r) * SWEEP_STAGE_PITCH + col];
+            const long long w = w0 + r, m = mb + col;
+            if (w < A.nw && m < m1) A.out[v][(w + A.g) * A.pitch_out + (m + A.g)] = val;
+        }
+    }
+    __syncwarp();
+}
+
+template <class R, int RL, int PROJ, int EOS>
+__global__ void __launch_bounds__(SWEEP_TPB) sweep_kernel(const SweepArgs A)
+{
+    __shared__ double stage_all[(SWEEP_TPB / 32) * 4 * 32 * SWEEP_STAGE_PITCH];
+    double *stage = stage_all + (threadIdx.x / 32) * (4 * 32 * SWEEP_STAGE_PITCH);
+
+    const long long w = (long long)blockIdx.x * SWEEP_TPB + threadIdx.x;
+    const long long w0 = (long long)blockIdx.x * SWEEP_TPB + (threadIdx.x & ~31);
+    const long long m0 = (long long)blockIdx.y * A.seg;
+    const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
+
+    SweepThread T;
+    T.valid = w < A.nw;
+    T.col = (T.valid ? w : A.nw - 1) + A.g;
+    T.amax = 0ULL; T.tmax = 0ULL;
+
+    const DeviceTimeState *ts = A.ts;
+    if (ts->done) {
+        // Past maxtime / maxcycle: the cycle is a no-op for the physics (src/solver.jl:333); keep the buffer
+        // rotation of the host bookkeeping consistent by copying the state through.
+        if (T.valid) {
+            for (long long m = m0; m < m1; m++) {
+                const long long i = (m + A.g) * A.pitch_in + T.col;
+                const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
+#pragma unroll
+                for (int k = 0; k < 4; k++) A.out[k][o] = A.in[k][i];
+            }
+        }
+        return;
+    }
+    const R dt = R(ts->current_dt) * R(A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
+
+    Pipe<R> P;
+    double in[4][4];
+    const long long a_begin = m0 - 4;
+    const long long nchunks = (m1 - m0 + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
+    const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed (clamped inside march_row)
+
+#pragma unroll
+    for (int j = 0; j < 4; j++) issue_loads(A, T, a_begin + j, in[j]);
+
+    // the pipeline registers start with finite dummies: warm-up results are never emitted
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.); P.cut[j] = R(0.); P.cE[j] = R(1.); P.cc[j] = R(1.);
+        P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
+        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
+        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
+    }
+    P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
+
+    long long a = a_begin;
+    // warm-up: 8 steps fill the dependency cone of the first output
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        march_step<R, RL, PROJ, EOS, 0, false>(A, T, P, in, a + 0, a_last, dt, 0, m1, stage);
+        march_step<R, RL, PROJ, EOS, 1, false>(A, T, P, in, a + 1, a_last, dt, 0, m1, stage);
+        march_step<R, RL, PROJ, EOS, 2, false>(A, T, P, in, a + 2, a_last, dt, 0, m1, stage);
+        march_step<R, RL, PROJ, EOS, 3, false>(A, T, P, in, a + 3, a_last, dt, 0, m1, stage);
+        a += 4;
+    }
+    // steady state: 8 outputs per iteration
+#pragma unroll 1
+    for (long long ch = 0; ch < nchunks; ch++) {
+        march_step<R, RL, PROJ, EOS, 0, true>(A, T, P, in, a + 0, a_last, dt, 0, m1, stage);
+        march_step<R, RL, PROJ, EOS, 1, true>(A, T, P, in, a + 1, a_last, dt, 1, m1, stage);
+        march_step<R, RL, PROJ, EOS, 2, true>(A, T, P, in, a + 2, a_last, dt, 2, m1, stage);
+        march_step<R, RL, PROJ, EOS, 3, true>(A, T, P, in, a + 3, a_last, dt, 3, m1, stage);
+        march_step<R, RL, PROJ, EOS, 0, true>(A, T, P, in, a + 4, a_last, dt, 4, m1, stage);
+        march_step<R, RL, PROJ, EOS, 1, true>(A, T, P, in, a + 5, a_last, dt, 5, m1, stage);
+        march_step<R, RL, PROJ, EOS, 2, true>(A, T, P, in, a + 6, a_last, dt, 6, m1, stage);
+        march_step<R, RL, PROJ, EOS, 3, true>(A, T, P, in, a + 7, a_last, dt, 7, m1, stage);
+        if (A.transpose_out) flush_stage(A, stage, w0, a - 4, m1);
+        a += 8;
+    }
+
+    // dtCFL partial maxima: warp shuffle, then one atomicMax per warp (max is order-independent: exact)
+    unsigned long long am = T.amax, tm = T.tmax;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);
+        const unsigned long long ot = __shfl_xor_sync(0xffffffffu, tm, off);
+        am = oa > am ? oa : am;
+        tm = ot > tm ? ot : tm;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&A.ts->acc[A.acc_slot][0], am);
+        atomicMax(&A.ts->acc[A.acc_slot][1], tm);
+    }
+}

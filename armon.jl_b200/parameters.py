@@ -216,7 +216,8 @@ class ArmonParameters:
         return options
 
     # -- init_backend(params, ::B200Device; options...), src/parameters.jl:758-778 ----------------
-    def _init_backend(self, math_mode="strict", march_segment=0, fused=True, device_id=None, **options):
+    def _init_backend(self, math_mode="strict", march_segment=0, fused=True, device_id=None, bind_pcg=True,
+                      **options):
         """Backend-specific options (like `armon_cpp_lib_src`/`use_md_iter` for Kokkos, ext/ArmonKokkos.jl:83-89).
 
         math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle;
@@ -225,12 +226,14 @@ class ArmonParameters:
         fused         True: one marching kernel per sweep (`solver_cycle` overload);
                       False: one kernel per reference kernel (the per-step overloads / `compare` path).
         device_id     CUDA ordinal; default LOCAL_RANK (one process per GPU).
+        bind_pcg      keep p, c, g arrays so that the stale `p` the reference saves can be produced.
         """
         if math_mode not in ("strict", "fast"):
             solver_error("config", f"unknown math_mode '{math_mode}'")
         self.math_mode = math_mode
         self.march_segment = int(march_segment)
         self.fused = bool(fused)
+        self.bind_pcg = bool(bind_pcg)
         self.device_id = int(os.environ.get("LOCAL_RANK", 0)) if device_id is None else int(device_id)
         self.backend_options = None   # set by BlockGrid / armon(): the library context
         return options
