@@ -14,8 +14,8 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libarmon_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "armon_b200.h")
 
-ARMON_OK, ARMON_ERR_INVALID, ARMON_ERR_CUDA, ARMON_ERR_NCCL, ARMON_ERR_TIME, ARMON_ERR_NO_DEVICE = range(6)
-MATH_MODES = {"strict": 0, "fast": 1}
+ARMON_OK, ARMON_ERR_INVALID, ARMON_ERR_CUDA, ARMON_ERR_NCCL, ARMON_ERR_TIME, ARMON_ERR_NO_DEVICE, ARMON_ERR_RANGE = range(7)
+MATH_MODES = {"strict": 0, "fast": 1, "ieee": 2}
 
 PD = C.POINTER(C.c_double)
 
@@ -98,6 +98,9 @@ SIGNATURES = {
     "armon_solver_halo_exchange": [_VP, C.c_int],
     "armon_solver_elapsed_ms": [_VP, C.POINTER(C.c_float)],
     "armon_solver_sweep_launches": [_VP, C.POINTER(C.c_uint64)],
+    "armon_solver_profile": [_VP, C.c_int],
+    "armon_solver_sweep_time_ms": [_VP, PD, C.POINTER(C.c_uint64)],
+    "armon_selftest_math": [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64 * 5)],
     "armon_comm_unique_id": [C.c_char * 128],
     "armon_ctx_comm_init": [_VP, C.c_char * 128, C.c_int, C.c_int],
     "armon_ctx_comm_destroy": [_VP],
@@ -109,15 +112,34 @@ PLAIN = {"armon_b200_abi_version": C.c_int, "armon_flt_size": C.c_int, "armon_id
 _lib = None
 
 
+def _preload_nccl():
+    """libarmon_b200.so needs `libnccl.so.2`.  When PyTorch is installed, load ITS bundled NCCL first so that a
+    later `import torch` in the same process (torch.distributed is the rank bootstrap) finds the version it was
+    built against instead of the older system library.  Without PyTorch the system libnccl.so.2 is used."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec is not None and spec.submodule_search_locations:
+            for loc in spec.submodule_search_locations:
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                    return cand
+    except Exception:
+        pass
+    return None
+
+
 def load_library(path=None):
     """dlopen the C-ABI library and declare its prototypes.  Raises if it is missing (no fallback)."""
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("ARMON_B200_LIB") or LIB_PATH   # ARMON_B200_LIB: kernel-variant experiments
     if not os.path.exists(path):
         solver_error("cpp", f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(make -C armon.jl_b200/csrc); the B200 backend has no CPU fallback")
+    _preload_nccl()
     lib = C.CDLL(path)
     for name, restype in PLAIN.items():
         fn = getattr(lib, name)
@@ -146,6 +168,24 @@ def device_count():
     return n.value if status == ARMON_OK else 0
 
 
+class _CtxHandle:
+    """Owns the library context.  Device arrays and solvers keep a strong reference to the handle inside their own
+    finalisers, so the context is destroyed only after everything allocated on it has been released, whatever the
+    order in which the garbage collector finalises a dropped object graph."""
+
+    def __init__(self, lib, ctx):
+        self.lib, self.ctx = lib, ctx
+        self._finalizer = weakref.finalize(self, lib.armon_ctx_destroy, ctx)
+
+
+def _free_array(handle, ptr):
+    handle.lib.armon_free(handle.ctx, ptr)
+
+
+def _destroy_solver(handle, solver):
+    handle.lib.armon_solver_destroy(solver)   # `handle` is only kept alive until here
+
+
 class B200Device:
     """`create_device(::Val{:B200})` (src/parameters.jl:738-755): a CUDA context + streams on one B200."""
 
@@ -155,7 +195,7 @@ class B200Device:
         check(self.lib.armon_ctx_create(int(device_id), C.byref(self._ctx)), "armon_ctx_create")
         self.device_id = int(device_id)
         self.rank, self.nranks = 0, 1
-        self._finalizer = weakref.finalize(self, self.lib.armon_ctx_destroy, self._ctx)
+        self.handle = _CtxHandle(self.lib, self._ctx)
 
     @property
     def ctx(self):
@@ -195,6 +235,13 @@ class B200Device:
     def array(self, n):
         return B200Array(self, n)
 
+    def selftest_math(self, n_samples=1 << 26, seed=1):
+        """(division, sqrt, shared-reciprocal, spurious-flag, missed-flag) mismatch counts of the strict-mode
+        division / sqrt against nvcc's IEEE instructions; all zero when healthy."""
+        out = (C.c_uint64 * 5)()
+        check(self.lib.armon_selftest_math(self._ctx, int(seed), int(n_samples), C.byref(out)), "armon_selftest_math")
+        return tuple(out)
+
 
 class B200Array:
     """`device_array_type(::B200Device)`: a 1-D Float64 device array owned by the host object
@@ -205,7 +252,7 @@ class B200Array:
         self.n = int(n)
         self._ptr = _VP()
         check(device.lib.armon_alloc(device.ctx, self.n, C.byref(self._ptr)), "armon_alloc")
-        self._finalizer = weakref.finalize(self, device.lib.armon_free, device.ctx, self._ptr)
+        self._finalizer = weakref.finalize(self, _free_array, device.handle, self._ptr)
 
     @property
     def ptr(self):

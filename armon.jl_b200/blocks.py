@@ -6,6 +6,7 @@ until asked for, p, c, g) are allocated on first access so that production runs 
 ping-pong (rho, u, v, E + work_1..4).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -89,6 +90,9 @@ class BlockGrid:
         self.params = params
         self.device = device or params.backend_options or B200Device(params.device_id)
         params.backend_options = self.device
+        if params.use_MPI and params.proc_size > 1 and self.device.nranks == 1:
+            from .distributed import setup_device_comm
+            setup_device_comm(params, self.device)
         self.lib = self.device.lib
         nx, ny = params.N
         g = params.nghost
@@ -111,6 +115,8 @@ class BlockGrid:
             s = C.c_void_p()
             check(self.lib.armon_solver_create(self.device.ctx, C.byref(self._desc), C.byref(s)), "armon_solver_create")
             self._solver = s
+            # the finaliser keeps the context handle alive until the solver is destroyed
+            self._solver_finalizer = weakref.finalize(self, backend._destroy_solver, self.device.handle, s)
             d = self.device_data
             main = (C.c_void_p * 4)(d.rho.ptr, d.u.ptr, d.v.ptr, d.E.ptr)
             work = (C.c_void_p * 4)(d.work_1.ptr, d.work_2.ptr, d.work_3.ptr, d.work_4.ptr)
@@ -138,7 +144,7 @@ class BlockGrid:
 
     def close(self):
         if self._solver is not None:
-            self.lib.armon_solver_destroy(self._solver)
+            self._solver_finalizer()
             self._solver = None
 
     # -- host <-> device -----------------------------------------------------------------------------------

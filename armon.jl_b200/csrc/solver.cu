@@ -24,6 +24,8 @@ __global__ void k_ts_reset(DeviceTimeState *ts, int cst_dt, double Dt)
     ts->next_cycle_dt = __longlong_as_double(0x7FF0000000000000LL);
     ts->error = 0;
     ts->done = 0;
+    ts->range_error = 0;
+    ts->redo_count = 0u;
     ts->acc[0][0] = ts->acc[0][1] = ts->acc[1][0] = ts->acc[1][1] = 0ULL;
 }
 
@@ -98,8 +100,9 @@ __global__ void k_init_dt(long long n_rows, long long n_cols, long long pitch, i
     if (col < n_cols && r < n_rows) {
         const long long i = (r + g) * pitch + (col + g);
         sd p, c, gg;
-        if (EOS == ARMON_EOS_BIZARRIUM) eos_bizarrium<sd, false>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, gg);
-        else eos_perfect_gas<sd>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c);
+        RangeFlag f;
+        if (EOS == ARMON_EOS_BIZARRIUM) eos_bizarrium<sd, DIV_IEEE, false>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, gg, f);
+        else eos_perfect_gas<sd, DIV_IEEE>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, f);
         bx = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(u[i]), c.v));
         by = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(v[i]), c.v));
     }
@@ -150,10 +153,11 @@ __global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, 
     const long long io = (iy + g) * (nx + 2 * g) + (ix + g);
     const long long ii = in_transposed ? (ix + g) * (ny + 2 * g) + (iy + g) : io;
     sd pp, cc, g_;
+    RangeFlag f;
     if (EOS == ARMON_EOS_BIZARRIUM) {
-        eos_bizarrium<sd, true>(sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc, g_);
+        eos_bizarrium<sd, DIV_IEEE, true>(sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc, g_, f);
     } else {
-        eos_perfect_gas<sd>(sd(gamma), sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc);
+        eos_perfect_gas<sd, DIV_IEEE>(sd(gamma), sd(rho[ii]), sd(u[ii]), sd(v[ii]), sd(E[ii]), pp, cc, f);
         g_ = (sd(1.) + sd(gamma)) / sd(2.);
     }
     if (p) p[io] = pp.v;
@@ -205,6 +209,10 @@ struct armon_solver {
     bool              timed = false;
     uint64_t          sweep_launches = 0;
     sweep_fn_t        kernel = nullptr;
+    // optional per-sweep-kernel timing (CUDA events on the launching stream), for the roofline figure
+    bool              profile = false;
+    std::vector<cudaEvent_t> prof_events;     // pairs (before, after) of each profiled sweep launch
+    size_t            prof_used = 0;
 };
 
 namespace {
@@ -333,8 +341,23 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     A.acc_slot = last_of_cycle ? 0 : 1;
 
     const dim3 grid((unsigned)((A.nw + SWEEP_TPB - 1) / SWEEP_TPB), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (s->profile) {
+        if (s->prof_used + 2 > s->prof_events.size()) {
+            for (int k = 0; k < 2; k++) {
+                cudaEvent_t e;
+                ARMON_CUDA(cudaEventCreate(&e));
+                s->prof_events.push_back(e);
+            }
+        }
+        ev0 = s->prof_events[s->prof_used];
+        ev1 = s->prof_events[s->prof_used + 1];
+        s->prof_used += 2;
+        ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
+    }
     s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
     ARMON_LAUNCH_CHECK(s->ctx);
+    if (s->profile) ARMON_CUDA(cudaEventRecord(ev1, s->ctx->stream));
     s->sweep_launches++;
 
     s->have_prev = true;
@@ -446,7 +469,8 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     ARMON_CHECK_ARG(desc->projection == ARMON_PROJ_EULER || desc->projection == ARMON_PROJ_EULER_2ND, "projection");
     ARMON_CHECK_ARG(desc->splitting >= 0 && desc->splitting <= 4, "axis splitting");
     ARMON_CHECK_ARG(desc->tc.eos == ARMON_EOS_PERFECT_GAS || desc->tc.eos == ARMON_EOS_BIZARRIUM, "EOS");
-    ARMON_CHECK_ARG(desc->math_mode == ARMON_MATH_STRICT || desc->math_mode == ARMON_MATH_FAST, "math mode");
+    ARMON_CHECK_ARG(desc->math_mode == ARMON_MATH_STRICT || desc->math_mode == ARMON_MATH_FAST ||
+                    desc->math_mode == ARMON_MATH_IEEE, "math mode");
     ARMON_CHECK_ARG(!desc->cst_dt || desc->Dt != 0.0, "Dt == 0 with constant step enabled");
 
     armon_solver *s = new armon_solver();
@@ -456,6 +480,8 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     const bool biz = desc->tc.eos == ARMON_EOS_BIZARRIUM;
     if (desc->math_mode == ARMON_MATH_STRICT)
         s->kernel = biz ? sweep_table_strict_biz(rl, desc->projection) : sweep_table_strict_pg(rl, desc->projection);
+    else if (desc->math_mode == ARMON_MATH_IEEE)
+        s->kernel = biz ? sweep_table_ieee_biz(rl, desc->projection) : sweep_table_ieee_pg(rl, desc->projection);
     else
         s->kernel = biz ? sweep_table_fast_biz(rl, desc->projection) : sweep_table_fast_pg(rl, desc->projection);
     if (!s->kernel) {
@@ -480,6 +506,7 @@ int armon_solver_destroy(armon_solver *s)
     if (s->ts) cudaFree(s->ts);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     delete s;
     return ARMON_OK;
 }
@@ -559,6 +586,11 @@ int armon_solver_time_loop(armon_solver *s)
     if (int rc = enqueue_cycle(s)) return rc;
     for (;;) {
         if (int rc = read_state(s, &st)) return rc;
+        if (st.error == ARMON_ERR_RANGE) {
+            armon_set_error("cycle %lld: a division/sqrt operand left [2^-500, 2^500]; rerun with math_mode ieee",
+                            (long long)st.cycle);
+            return ARMON_ERR_RANGE;
+        }
         if (st.error) {
             armon_set_error("Invalid time step for cycle %lld", (long long)st.cycle);
             return ARMON_ERR_TIME;
@@ -630,6 +662,30 @@ int armon_solver_elapsed_ms(armon_solver *s, float *ms)
     ARMON_CHECK_ARG(s->timed, "no armon_solver_run / armon_solver_time_loop call to time");
     ARMON_CUDA(cudaEventSynchronize(s->ev_stop));
     ARMON_CUDA(cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
+    return ARMON_OK;
+}
+
+int armon_solver_profile(armon_solver *s, int enable)
+{
+    if (int rc = solver_check(s, false)) return rc;
+    s->profile = enable != 0;
+    s->prof_used = 0;
+    return ARMON_OK;
+}
+
+int armon_solver_sweep_time_ms(armon_solver *s, double *total_ms, uint64_t *count)
+{
+    if (int rc = solver_check(s, false)) return rc;
+    ARMON_CHECK_ARG(total_ms && count, "null result");
+    ARMON_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    double total = 0.0;
+    for (size_t k = 0; k + 1 < s->prof_used; k += 2) {
+        float ms = 0.f;
+        ARMON_CUDA(cudaEventElapsedTime(&ms, s->prof_events[k], s->prof_events[k + 1]));
+        total += ms;
+    }
+    *total_ms = total;
+    *count = s->prof_used / 2;
     return ARMON_OK;
 }
 

@@ -43,7 +43,8 @@ __global__ void k_perfect_gas_EOS(Dom D, double gamma, const double *rho, const 
     int64_t i;
     if (!cell_of_thread(D, i)) return;
     sd pp, cc;
-    eos_perfect_gas<sd>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), pp, cc);
+    RangeFlag f;
+    eos_perfect_gas<sd, DIV_IEEE>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), pp, cc, f);
     p[i] = pp.v;
     c[i] = cc.v;
     g[i] = ((sd(1.) + sd(gamma)) / sd(2.)).v;
@@ -56,7 +57,8 @@ __global__ void k_bizarrium_EOS(Dom D, const double *rho, const double *u, const
     int64_t i;
     if (!cell_of_thread(D, i)) return;
     sd pp, cc, gg;
-    eos_bizarrium<sd, true>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), pp, cc, gg);
+    RangeFlag f;
+    eos_bizarrium<sd, DIV_IEEE, true>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), pp, cc, gg, f);
     p[i] = pp.v;
     c[i] = cc.v;
     g[i] = gg.v;
@@ -95,8 +97,9 @@ __global__ void k_acoustic(Dom D, int64_t s, double *us, double *ps, const doubl
     int64_t i;
     if (!cell_of_thread(D, i)) return;
     sd a, b;
-    acoustic_godunov<sd>(sd(rho[i - s]) * sd(c[i - s]), sd(rho[i]) * sd(c[i]), sd(u[i - s]), sd(u[i]),
-                         sd(p[i - s]), sd(p[i]), a, b);
+    RangeFlag f;
+    acoustic_godunov<sd, DIV_IEEE>(sd(rho[i - s]) * sd(c[i - s]), sd(rho[i]) * sd(c[i]), sd(u[i - s]), sd(u[i]),
+                                   sd(p[i - s]), sd(p[i]), a, b, f);
     us[i] = a.v;
     ps[i] = b.v;
 }
@@ -115,9 +118,10 @@ __global__ void k_acoustic_GAD(Dom D, int64_t s, double dt_, double dx_, double 
     const sd p_mm(p[i - 2 * s]), p_m(p[i - s]), p_0(p[i]), p_p(p[i + s]);
 
     sd us_im, ps_im, us_i, ps_i, us_ip, ps_ip;
-    acoustic_godunov<sd>(r_mm * c_mm, r_m * c_m, u_mm, u_m, p_mm, p_m, us_im, ps_im);
-    acoustic_godunov<sd>(r_m * c_m, r_0 * c_0, u_m, u_0, p_m, p_0, us_i, ps_i);
-    acoustic_godunov<sd>(r_0 * c_0, r_p * c_p, u_0, u_p, p_0, p_p, us_ip, ps_ip);
+    RangeFlag f;
+    acoustic_godunov<sd, DIV_IEEE>(r_mm * c_mm, r_m * c_m, u_mm, u_m, p_mm, p_m, us_im, ps_im, f);
+    acoustic_godunov<sd, DIV_IEEE>(r_m * c_m, r_0 * c_0, u_m, u_0, p_m, p_0, us_i, ps_i, f);
+    acoustic_godunov<sd, DIV_IEEE>(r_0 * c_0, r_p * c_p, u_0, u_p, p_0, p_p, us_ip, ps_ip, f);
 
     sd r_um = (us_ip - u_0) / ((us_i - u_m) + sd(1e-6));
     sd r_pm = (ps_ip - p_0) / ((ps_i - p_m) + sd(1e-6));

@@ -6,19 +6,21 @@
 typedef void (*sweep_fn_t)(const SweepArgs);
 
 // rl: 0 = Godunov (acoustic!), 1 + limiter code = GAD with that limiter; proj: ARMON_PROJ_*
+sweep_fn_t sweep_table_ieee_pg(int rl, int proj);
+sweep_fn_t sweep_table_ieee_biz(int rl, int proj);
 sweep_fn_t sweep_table_strict_pg(int rl, int proj);
 sweep_fn_t sweep_table_strict_biz(int rl, int proj);
 sweep_fn_t sweep_table_fast_pg(int rl, int proj);
 sweep_fn_t sweep_table_fast_biz(int rl, int proj);
 
-#define ARMON_DEFINE_SWEEP_TABLE(NAME, R, EOS)                                              \
+#define ARMON_DEFINE_SWEEP_TABLE(NAME, R, DIV, EOS)                                          \
     sweep_fn_t NAME(int rl, int proj)                                                       \
     {                                                                                       \
         static const sweep_fn_t table[4][2] = {                                             \
-            {sweep_kernel<R, 0, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_kernel<R, 1, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_kernel<R, 2, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_kernel<R, 3, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
         return table[rl][proj];                                                             \

@@ -1,3 +1,3 @@
-// Instantiations of the fused sweep kernel: arithmetic fd, EOS ARMON_EOS_PERFECT_GAS.
+// Instantiations of the fused sweep kernel: number type fd, division policy DIV_FAST, EOS ARMON_EOS_PERFECT_GAS.
 #include "sweep_dispatch.h"
-ARMON_DEFINE_SWEEP_TABLE(sweep_table_fast_pg, fd, ARMON_EOS_PERFECT_GAS)
+ARMON_DEFINE_SWEEP_TABLE(sweep_table_fast_pg, fd, DIV_FAST, ARMON_EOS_PERFECT_GAS)

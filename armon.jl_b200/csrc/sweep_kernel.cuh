@@ -25,7 +25,8 @@
 // The expression order of the reference source is kept; with R = sd every operation is an
 // explicitly rounded IEEE operation and the result is bit-identical to the strict CPU oracle.  Only rewrites that
 // are exact in IEEE arithmetic are applied: x/2 -> x*0.5, x/dx -> x*(1/dx) when dx is a power of two,
-// s*x with s = sign(..) in {-1,0,1} -> sign-bit flips, max(|u+c|,|u-c|) -> |u|+c for c >= 0.
+// s*x with s = sign(..) in {-1,0,1} -> sign-bit flips, max(|u+c|,|u-c|) -> |u|+c for c >= 0, one refined reciprocal
+// shared by the quotients that have the same divisor, and a branch-free correctly rounded division (common.cuh).
 #pragma once
 
 #include "common.cuh"
@@ -72,18 +73,14 @@ template <class R> __device__ __forceinline__ R slope_minmod_fused(R qm, R q0, R
     return R(d_p.v == 0.0 ? 0.0 : res);
 }
 
-template <class R> __device__ __forceinline__ R div_by_dx(R x, const SweepArgs &A)
-{
-    return A.dx_pow2 ? x * R(A.inv_dx) : x / R(A.dx);
-}
-
-template <class R, int EOS> __device__ __forceinline__ void eos_eval(const SweepArgs &A, R rho, R ua, R ut, R E, R &p, R &c)
+template <class R, int DIV, int EOS>
+__device__ __forceinline__ void eos_eval(const SweepArgs &A, R rho, R ua, R ut, R E, R &p, R &c, RangeFlag &f)
 {
     if (EOS == ARMON_EOS_BIZARRIUM) {
         R g;
-        eos_bizarrium<R, false>(rho, ua, ut, E, p, c, g);
+        eos_bizarrium<R, DIV, false>(rho, ua, ut, E, p, c, g, f);
     } else {
-        eos_perfect_gas<R>(R(A.gamma), rho, ua, ut, E, p, c);
+        eos_perfect_gas<R, DIV>(R(A.gamma), rho, ua, ut, E, p, c, f);
     }
 }
 
@@ -101,35 +98,42 @@ template <class R> struct Pipe {
 struct SweepThread {
     long long col;         // element offset of this thread's column inside a row (w + g)
     bool      valid;       // column holds a real cell
+    const double *base[4]; // A.in[k] + col
     unsigned long long amax, tmax;   // dt accumulators (integer images of non-negative doubles)
+    RangeFlag flag;        // range bookkeeping of the branch-free divisions (DIV_FLAGGED)
 };
 
-__device__ __forceinline__ long long march_row(const SweepArgs &A, long long a)
+// element offset of the first cell of array row `a` (march index, may be a ghost): mirrored at global edges
+// (boundary_conditions!, src/halo_exchange.jl:2-29), clamped so that prefetches past the last needed row and the
+// tail of a ragged last chunk stay inside the array.  Warp-uniform.
+__device__ __forceinline__ long long march_row_offset(const SweepArgs &A, long long a)
 {
     long long r = a;
     if (a < 0 && A.mirror_lo) r = -1 - a;
     else if (a >= A.nm && A.mirror_hi) r = 2 * A.nm - 1 - a;
-    // clamp: prefetches past the last needed row (and mirrors of a ragged last chunk) stay inside the array
     const long long rmax = A.nm + A.g - 1, rmin = -(long long)A.g;
     r = r > rmax ? rmax : (r < rmin ? rmin : r);
-    return r + A.g;
+    return (r + A.g) * A.pitch_in;
 }
 
 __device__ __forceinline__ void issue_loads(const SweepArgs &A, const SweepThread &T, long long a, double v[4])
 {
-    const long long idx = march_row(A, a) * A.pitch_in + T.col;
+    const long long off = march_row_offset(A, a);
 #pragma unroll
-    for (int k = 0; k < 4; k++) v[k] = __ldg(A.in[k] + idx);
+    for (int k = 0; k < 4; k++) v[k] = __ldg(T.base[k] + off);
 }
 
-// One march step: consumes cell a (already in `in`), emits cell a-4.  J = (a - a_begin) & 3 is static.
-template <class R, int RL, int PROJ, int EOS, int J, bool EMIT>
+// One march step: consumes cell a (already in `in`), emits cell a-4 when `emit`.  J = (a - a_begin) & 3 is static.
+template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED, int J>
 __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, Pipe<R> &P, double (&in)[4][4],
                                            const long long a, const long long a_last, const R dt,
+                                           const typename Div<R, DIV>::Rcp &inv_dx, const bool emit,
                                            const int k_chunk, const long long m1, double *stage)
 {
+    typedef Div<R, DIV> D;
     constexpr int S0 = J & 3, S1 = (J + 3) & 3, S2 = (J + 2) & 3, S3 = (J + 1) & 3;
     const R dx(A.dx);
+    RangeFlag &f = T.flag;
 
     // ---- cell a: boundary factors, EOS (src/kernels.jl:4-55) ----
     R rho(in[J][0]), ua(in[J][1]), ut(in[J][2]), E(in[J][3]);
@@ -142,12 +146,12 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
     }
     const R c_out = P.cc[S0];   // c of cell a-4 (EOS at the start of this sweep), read before the slot is reused
     R p, c;
-    eos_eval<R, EOS>(A, rho, ua, ut, E, p, c);
+    eos_eval<R, DIV, EOS>(A, rho, ua, ut, E, p, c, f);
     const R rc = rho * c;
     P.cu[S0] = ua; P.cp[S0] = p; P.crc[S0] = rc; P.cdm[S0] = rho * dx; P.cut[S0] = ut; P.cE[S0] = E; P.cc[S0] = c;
 
     // ---- Godunov state at interface a (cells a-1, a): src/riemann_schemes.jl:21-30 ----
-    acoustic_godunov<R>(P.crc[S1], rc, P.cu[S1], ua, P.cp[S1], p, P.Gu[S0], P.Gp[S0]);
+    acoustic_godunov<R, DIV>(P.crc[S1], rc, P.cu[S1], ua, P.cp[S1], p, P.Gu[S0], P.Gp[S0], f);
 
     // ---- flux at interface i = a-1 (cells a-2, a-1) ----
     if (RL == 0) {   // acoustic!  src/riemann_schemes.jl:33-43
@@ -157,16 +161,15 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
         constexpr int LIM = RL - 1;
         const R u_i = P.cu[S1], u_im = P.cu[S2], p_i = P.cp[S1], p_im = P.cp[S2];
         const R us_i = P.Gu[S1], ps_i = P.Gp[S1];
-        R r_um = (P.Gu[S0] - u_i) / ((us_i - u_im) + R(1e-6));
-        R r_pm = (P.Gp[S0] - p_i) / ((ps_i - p_im) + R(1e-6));
-        R r_up = (u_im - P.Gu[S2]) / ((u_i - us_i) + R(1e-6));
-        R r_pp = (p_im - P.Gp[S2]) / ((p_i - ps_i) + R(1e-6));
-        r_um = limiter<R, LIM>(r_um);
-        r_pm = limiter<R, LIM>(r_pm);
-        r_up = limiter<R, LIM>(r_up);
-        r_pp = limiter<R, LIM>(r_pp);
+        R r_um(1.), r_pm(1.), r_up(1.), r_pp(1.);
+        if (LIM != ARMON_LIMITER_NONE) {   // limiter(r, NoLimiter) == 1 whatever r is (src/limiters.jl:6)
+            r_um = limiter<R, LIM>(D::div(P.Gu[S0] - u_i, (us_i - u_im) + R(1e-6), f));
+            r_pm = limiter<R, LIM>(D::div(P.Gp[S0] - p_i, (ps_i - p_im) + R(1e-6), f));
+            r_up = limiter<R, LIM>(D::div(u_im - P.Gu[S2], (u_i - us_i) + R(1e-6), f));
+            r_pp = limiter<R, LIM>(D::div(p_im - P.Gp[S2], (p_i - ps_i) + R(1e-6), f));
+        }
         const R Dm = (P.cdm[S2] + P.cdm[S1]) * R(0.5);                                   // (dm_l + dm_r) / 2
-        const R theta = R(0.5) * (R(1.) - ((P.crc[S2] + P.crc[S1]) * R(0.5)) * (dt / Dm));
+        const R theta = R(0.5) * (R(1.) - ((P.crc[S2] + P.crc[S1]) * R(0.5)) * D::div(dt, Dm, f));
         P.Fu[S1] = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
         P.Fp[S1] = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
     }
@@ -177,8 +180,8 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
     {
         const R dxl = dx + dt * (P.Fu[S1] - P.Fu[S2]);
         const R dm = P.cdm[S2];
-        const R dtdm = dt / dm;
-        const R Lr = dm / dxl;
+        const R dtdm = D::div(dt, dm, f);
+        const R Lr = D::div(dm, dxl, f);
         const R Lu = P.cu[S2] + dtdm * (P.Fp[S2] - P.Fp[S1]);
         const R LE = P.cE[S2] + dtdm * (P.FpFu[S2] - P.FpFu[S1]);
         const R Lt = P.cut[S2];
@@ -198,9 +201,9 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
             const R dxl_0 = rsel(pos, P.dxl[S0], P.dxl[S3]);
             const R dxl_p = rsel(pos, P.dxl[S3], P.dxl[S2]);
             const R two_dxl = R(2.) * dxl_0;
-            const R r_m = two_dxl / (dxl_0 + dxl_m);
-            const R r_p = two_dxl / (dxl_0 + dxl_p);
-            const R lf = dxe / two_dxl;
+            const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
+            const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
+            const R lf = D::div(dxe, two_dxl, f);
 #define ARMON_ADVECT(q, res)                                                                         \
             {                                                                                        \
                 const R qm = rsel(pos, P.q[S1], P.q[S0]);                                            \
@@ -222,13 +225,21 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
     }
 
     // ---- projection of cell k = a-4: src/projection_schemes.jl:23-41 ----
-    if (EMIT) {
+    if (emit) {
         const R dXr = P.dxl[S0] * P.Lr[S0];
-        const R t_r = div_by_dx<R>(dXr - (Anr - P.Ar), A);
-        const R t_ru = div_by_dx<R>(dXr * P.Lu[S0] - (Anru - P.Aru), A);
-        const R t_rt = div_by_dx<R>(dXr * P.Lt[S0] - (Anrt - P.Art), A);
-        const R t_rE = div_by_dx<R>(dXr * P.LE[S0] - (AnrE - P.ArE), A);
-        const R o_ua = t_ru / t_r, o_ut = t_rt / t_r, o_E = t_rE / t_r;
+        R t_r = dXr - (Anr - P.Ar);
+        R t_ru = dXr * P.Lu[S0] - (Anru - P.Aru);
+        R t_rt = dXr * P.Lt[S0] - (Anrt - P.Art);
+        R t_rE = dXr * P.LE[S0] - (AnrE - P.ArE);
+        if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
+            const R idx(A.inv_dx);
+            t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
+        } else {
+            t_r = D::quot(t_r, inv_dx, f); t_ru = D::quot(t_ru, inv_dx, f);
+            t_rt = D::quot(t_rt, inv_dx, f); t_rE = D::quot(t_rE, inv_dx, f);
+        }
+        const typename D::Rcp inv_r = D::prepare(t_r, f);
+        const R o_ua = D::quot(t_ru, inv_r, f), o_ut = D::quot(t_rt, inv_r, f), o_E = D::quot(t_rE, inv_r, f);
         const long long m = a - 4;
         const bool store = T.valid && m < m1;
         // dtCFL accumulators (src/reductions.jl:14-20): max(|u+c|,|u-c|) == |u|+c, new velocities, c of this sweep's EOS
@@ -238,7 +249,7 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
             T.amax = ba > T.amax ? ba : T.amax;
             T.tmax = bt > T.tmax ? bt : T.tmax;
         }
-        if (A.transpose_out) {
+        if (STAGED && A.transpose_out) {
             // stage[var][lane][k]: flushed as rows of SWEEP_CHUNK contiguous doubles by flush_stage()
             double *s = stage + (threadIdx.x & 31) * SWEEP_STAGE_PITCH + k_chunk;
             s[0 * 32 * SWEEP_STAGE_PITCH] = t_r.v;
@@ -246,7 +257,7 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
             s[2 * 32 * SWEEP_STAGE_PITCH] = o_ut.v;
             s[3 * 32 * SWEEP_STAGE_PITCH] = o_E.v;
         } else if (store) {
-            const long long o = (m + A.g) * A.pitch_out + T.col;
+            const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
             A.out[0][o] = t_r.v;
             A.out[1][o] = o_ua.v;
             A.out[2][o] = o_ut.v;
@@ -277,8 +288,57 @@ __device__ __forceinline__ void flush_stage(const SweepArgs &A, const double *st
     __syncwarp();
 }
 
-template <class R, int RL, int PROJ, int EOS>
-__global__ void __launch_bounds__(SWEEP_TPB) sweep_kernel(const SweepArgs A)
+// The march of one thread over one segment [m0, m1) of its column.  STAGED: transposed outputs go through the
+// warp's shared staging buffer (warp-collective; every lane of the warp must take part); otherwise every store is
+// a direct one (used by the per-thread IEEE recomputation).
+template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED>
+__device__ __forceinline__ void march_segment(const SweepArgs &A, SweepThread &T, const R dt, const long long m0,
+                                              const long long m1, const long long w0, double *stage)
+{
+    const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
+    Pipe<R> P;
+    double in[4][4];
+    const long long a_begin = m0 - 4;
+    const long long nchunks = (m1 - m0 + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
+    const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed (clamped inside march_row_offset)
+
+#pragma unroll
+    for (int j = 0; j < 4; j++) issue_loads(A, T, a_begin + j, in[j]);
+
+    // the pipeline registers start with finite dummies: warm-up results are never emitted
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.); P.cut[j] = R(0.); P.cE[j] = R(1.); P.cc[j] = R(1.);
+        P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
+        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
+        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
+    }
+    P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
+
+    // One loop body of 4 steps (the ring period).  The first 2 iterations only fill the dependency cone of the
+    // first output (8 warm-up cells); afterwards every iteration emits 4 cells and every second one flushes the
+    // transposed staging buffer.
+    long long a = a_begin;
+    const long long n_iter = 2 + 2 * nchunks;
+#pragma unroll 1
+    for (long long it = 0; it < n_iter; it++) {
+        const bool emit = it >= 2;
+        const int kc = (int)(it & 1) * 4;
+        march_step<R, DIV, RL, PROJ, EOS, STAGED, 0>(A, T, P, in, a + 0, a_last, dt, inv_dx, emit, kc + 0, m1, stage);
+        march_step<R, DIV, RL, PROJ, EOS, STAGED, 1>(A, T, P, in, a + 1, a_last, dt, inv_dx, emit, kc + 1, m1, stage);
+        march_step<R, DIV, RL, PROJ, EOS, STAGED, 2>(A, T, P, in, a + 2, a_last, dt, inv_dx, emit, kc + 2, m1, stage);
+        march_step<R, DIV, RL, PROJ, EOS, STAGED, 3>(A, T, P, in, a + 3, a_last, dt, inv_dx, emit, kc + 3, m1, stage);
+        a += 4;
+        if (STAGED && A.transpose_out && emit && (it & 1)) flush_stage(A, stage, w0, a - 12, m1);
+    }
+}
+
+#ifndef SWEEP_MIN_BLOCKS
+#define SWEEP_MIN_BLOCKS 2
+#endif
+
+template <class R, int DIV, int RL, int PROJ, int EOS>
+__global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_BLOCKS) sweep_kernel(const SweepArgs A)
 {
     __shared__ double stage_all[(SWEEP_TPB / 32) * 4 * 32 * SWEEP_STAGE_PITCH];
     double *stage = stage_all + (threadIdx.x / 32) * (4 * 32 * SWEEP_STAGE_PITCH);
@@ -291,6 +351,8 @@ __global__ void __launch_bounds__(SWEEP_TPB) sweep_kernel(const SweepArgs A)
     SweepThread T;
     T.valid = w < A.nw;
     T.col = (T.valid ? w : A.nw - 1) + A.g;
+#pragma unroll
+    for (int k = 0; k < 4; k++) T.base[k] = A.in[k] + T.col;
     T.amax = 0ULL; T.tmax = 0ULL;
 
     const DeviceTimeState *ts = A.ts;
@@ -309,48 +371,20 @@ __global__ void __launch_bounds__(SWEEP_TPB) sweep_kernel(const SweepArgs A)
     }
     const R dt = R(ts->current_dt) * R(A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
 
-    Pipe<R> P;
-    double in[4][4];
-    const long long a_begin = m0 - 4;
-    const long long nchunks = (m1 - m0 + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
-    const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed (clamped inside march_row)
+    march_segment<R, DIV, RL, PROJ, EOS, true>(A, T, dt, m0, m1, w0, stage);
 
-#pragma unroll
-    for (int j = 0; j < 4; j++) issue_loads(A, T, a_begin + j, in[j]);
-
-    // the pipeline registers start with finite dummies: warm-up results are never emitted
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.); P.cut[j] = R(0.); P.cE[j] = R(1.); P.cc[j] = R(1.);
-        P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
-        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
-        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
-    }
-    P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
-
-    long long a = a_begin;
-    // warm-up: 8 steps fill the dependency cone of the first output
-#pragma unroll 1
-    for (int it = 0; it < 2; it++) {
-        march_step<R, RL, PROJ, EOS, 0, false>(A, T, P, in, a + 0, a_last, dt, 0, m1, stage);
-        march_step<R, RL, PROJ, EOS, 1, false>(A, T, P, in, a + 1, a_last, dt, 0, m1, stage);
-        march_step<R, RL, PROJ, EOS, 2, false>(A, T, P, in, a + 2, a_last, dt, 0, m1, stage);
-        march_step<R, RL, PROJ, EOS, 3, false>(A, T, P, in, a + 3, a_last, dt, 0, m1, stage);
-        a += 4;
-    }
-    // steady state: 8 outputs per iteration
-#pragma unroll 1
-    for (long long ch = 0; ch < nchunks; ch++) {
-        march_step<R, RL, PROJ, EOS, 0, true>(A, T, P, in, a + 0, a_last, dt, 0, m1, stage);
-        march_step<R, RL, PROJ, EOS, 1, true>(A, T, P, in, a + 1, a_last, dt, 1, m1, stage);
-        march_step<R, RL, PROJ, EOS, 2, true>(A, T, P, in, a + 2, a_last, dt, 2, m1, stage);
-        march_step<R, RL, PROJ, EOS, 3, true>(A, T, P, in, a + 3, a_last, dt, 3, m1, stage);
-        march_step<R, RL, PROJ, EOS, 0, true>(A, T, P, in, a + 4, a_last, dt, 4, m1, stage);
-        march_step<R, RL, PROJ, EOS, 1, true>(A, T, P, in, a + 5, a_last, dt, 5, m1, stage);
-        march_step<R, RL, PROJ, EOS, 2, true>(A, T, P, in, a + 6, a_last, dt, 6, m1, stage);
-        march_step<R, RL, PROJ, EOS, 3, true>(A, T, P, in, a + 7, a_last, dt, 7, m1, stage);
-        if (A.transpose_out) flush_stage(A, stage, w0, a - 4, m1);
-        a += 8;
+    if (DIV == DIV_FLAGGED) {
+        // A thread whose operands left the range in which the branch-free division is proven exact (in practice:
+        // a tiny non-zero dividend in the decaying tail of the numerical domain of influence) recomputes its
+        // whole segment with nvcc's full IEEE division and overwrites its column: the strict mode is IEEE for
+        // every operand, the common path just never pays for the slow path.
+        range_check_dividend(dt.v, T.flag);
+        if (T.flag.bad()) {
+            T.amax = 0ULL; T.tmax = 0ULL;
+            march_segment<R, DIV_IEEE, RL, PROJ, EOS, false>(A, T, dt, m0, m1, w0, stage);
+            if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(&A.ts->redo_count, 1u);
+        }
+        __syncwarp();
     }
 
     // dtCFL partial maxima: warp shuffle, then one atomicMax per warp (max is order-independent: exact)

@@ -220,15 +220,17 @@ class ArmonParameters:
                       **options):
         """Backend-specific options (like `armon_cpp_lib_src`/`use_md_iter` for Kokkos, ext/ArmonKokkos.jl:83-89).
 
-        math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle;
-                      "fast": FMA contraction + shared reciprocals (the reference's own @fastmath latitude).
+        math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle (branch-free
+                      correctly rounded division, operands must stay in [2^-500, 2^500] or be 0, else :cpp error);
+                      "ieee": the same with nvcc's full IEEE division (every operand, slower);
+                      "fast": FMA contraction + reciprocal division (the reference's own @fastmath latitude).
         march_segment cells per marching segment along the swept axis (0 = auto).
         fused         True: one marching kernel per sweep (`solver_cycle` overload);
                       False: one kernel per reference kernel (the per-step overloads / `compare` path).
         device_id     CUDA ordinal; default LOCAL_RANK (one process per GPU).
         bind_pcg      keep p, c, g arrays so that the stale `p` the reference saves can be produced.
         """
-        if math_mode not in ("strict", "fast"):
+        if math_mode not in ("strict", "fast", "ieee"):
             solver_error("config", f"unknown math_mode '{math_mode}'")
         self.math_mode = math_mode
         self.march_segment = int(march_segment)

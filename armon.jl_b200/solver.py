@@ -209,6 +209,8 @@ def _sync_fused_state(params, grid):
     st = grid.time_state()
     gdt = grid.global_dt
     gdt.cycle, gdt.time, gdt.current_dt, gdt.next_cycle_dt = st.cycle, st.time, st.current_dt, st.next_cycle_dt
+    if st.error == backend.ARMON_ERR_RANGE:
+        solver_error("cpp", f"cycle {st.cycle}: a division/sqrt operand left [2^-500, 2^500]; rerun with math_mode='ieee'")
     if st.error:
         solver_error("time", f"Invalid time step for cycle {st.cycle}")
     return st

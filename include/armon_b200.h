@@ -38,7 +38,10 @@ enum {
     ARMON_ERR_CUDA = 2,      /* CUDA runtime failure                      -> SolverException(:cpp)    */
     ARMON_ERR_NCCL = 3,      /* NCCL failure                              -> SolverException(:cpp)    */
     ARMON_ERR_TIME = 4,      /* invalid time step, src/solver_state.jl:123-124 -> SolverException(:time) */
-    ARMON_ERR_NO_DEVICE = 5  /* no CUDA device: the backend has no CPU fallback */
+    ARMON_ERR_NO_DEVICE = 5, /* no CUDA device: the backend has no CPU fallback */
+    ARMON_ERR_RANGE = 6      /* math_mode strict: a division/sqrt operand left the range in which the branch-free
+                                correctly-rounded routines are exact (|x| in [2^-500, 2^500] or 0); rerun with
+                                math_mode ieee                                  -> SolverException(:cpp)    */
 };
 
 /* src/utils.jl:15-78 (Axis.X=1.. in Julia; 0-based here) */
@@ -54,8 +57,12 @@ enum { ARMON_SPLIT_SEQUENTIAL = 0, ARMON_SPLIT_GODUNOV = 1, ARMON_SPLIT_STRANG =
        ARMON_SPLIT_X_ONLY = 3, ARMON_SPLIT_Y_ONLY = 4 };                        /* src/axis_splitting.jl:2-5 */
 enum { ARMON_EOS_PERFECT_GAS = 0, ARMON_EOS_BIZARRIUM = 1 };                    /* src/kernels.jl:151-161 */
 /* arithmetic mode of the fused sweep kernels */
-enum { ARMON_MATH_STRICT = 0,   /* IEEE operation order of the reference source, no FMA contraction: bit-exact vs oracle */
-       ARMON_MATH_FAST = 1 };   /* FMA contraction + shared reciprocals, like the reference's @fastmath (src/generic_kernel.jl:2-4) */
+enum { ARMON_MATH_STRICT = 0,   /* IEEE operation order of the reference source, no FMA contraction, correctly rounded
+                                   branch-free division/sqrt: bit-exact vs the oracle; operands outside
+                                   [2^-500, 2^500] (other than 0) raise ARMON_ERR_RANGE instead of being mis-rounded */
+       ARMON_MATH_FAST = 1,     /* FMA contraction + reciprocal-based division (<= 2 ulp), like the reference's own
+                                   @fastmath kernels (src/generic_kernel.jl:2-4) */
+       ARMON_MATH_IEEE = 2 };   /* as STRICT but with nvcc's full IEEE division/sqrt (slow paths for every operand) */
 
 typedef struct armon_ctx armon_ctx;
 typedef struct armon_solver armon_solver;
@@ -226,8 +233,18 @@ int armon_solver_halo_exchange(armon_solver *solver, int axis);
 /* device time (ms, CUDA events on the solver's stream) spent in the cycles enqueued by the last
  * armon_solver_run / armon_solver_time_loop call; blocks until they finished */
 int armon_solver_elapsed_ms(armon_solver *solver, float *ms);
+/* Per-kernel timing of the sweep launches (CUDA events recorded on the solver's stream around every sweep kernel
+ * while enabled): `armon_solver_profile(s, 1)` starts a new measurement, `armon_solver_sweep_time_ms` blocks and
+ * returns the summed device time and the number of launches measured.  Used for bench.py's roofline figure. */
+int armon_solver_profile(armon_solver *solver, int enable);
+int armon_solver_sweep_time_ms(armon_solver *solver, double *total_ms, uint64_t *count);
 /* kernel + launch statistics of the fused path */
 int armon_solver_sweep_launches(armon_solver *solver, uint64_t *count);
+
+/* On-device self test: compares the branch-free division / sqrt of the strict mode with nvcc's IEEE div.rn.f64 /
+ * sqrt.rn.f64 on `n_samples` pseudo-random operand pairs.  mismatch = {division, sqrt, shared-reciprocal division,
+ * spurious range flags, missed range flags}; all must be 0. */
+int armon_selftest_math(armon_ctx *ctx, uint64_t seed, uint64_t n_samples, uint64_t mismatch[5]);
 
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU plumbing, replacing MPI.Cart_create / Startall / Iallreduce (src/parameters.jl:408-467,
