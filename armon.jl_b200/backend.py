@@ -45,7 +45,7 @@ class armon_solver_desc(C.Structure):
                 ("cfl", C.c_double), ("maxtime", C.c_double), ("maxcycle", C.c_int64),
                 ("cst_dt", C.c_int32), ("Dt", C.c_double),
                 ("neighbours", C.c_int32 * 4),
-                ("math_mode", C.c_int32), ("march_segment", C.c_int32),
+                ("math_mode", C.c_int32), ("march_segment", C.c_int32), ("kernel_variant", C.c_int32),
                 ("tc", armon_test_case)]
 
 

@@ -8,6 +8,8 @@
 #include "sweep_dispatch.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 namespace {
@@ -209,6 +211,12 @@ struct armon_solver {
     bool              timed = false;
     uint64_t          sweep_launches = 0;
     sweep_fn_t        kernel = nullptr;
+    // warp-specialised path (sweep_ws_kernel.cuh): main kernel + IEEE fix-up kernel (strict mode only)
+    sweep_ws_fn_t     ws_kernel = nullptr, fixup_kernel = nullptr;
+    bool              use_ws = false;
+    unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
+    unsigned long long *fix_list = nullptr;
+    uint64_t          sweep_index = 0;
     // optional per-sweep-kernel timing (CUDA events on the launching stream), for the roofline figure
     bool              profile = false;
     std::vector<cudaEvent_t> prof_events;     // pairs (before, after) of each profiled sweep launch
@@ -295,8 +303,9 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         return seg;
     }
     // as long as possible (8 warm-up rows per segment are redundant work) while keeping >= 6 waves of CTAs
-    const long long ncol = (nw + SWEEP_TPB - 1) / SWEEP_TPB;
-    const long long want = 6LL * 2 * s->ctx->sm_count;
+    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB, ctas_per_sm = s->use_ws ? 7 : 2;
+    const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
+    const long long want = 6LL * ctas_per_sm * s->ctx->sm_count;
     const int cands[] = {512, 256, 128, 64, 32, 16};
     for (int seg : cands) {
         if (seg > nm && seg != 16) continue;
@@ -340,7 +349,8 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     A.ts = s->ts;
     A.acc_slot = last_of_cycle ? 0 : 1;
 
-    const dim3 grid((unsigned)((A.nw + SWEEP_TPB - 1) / SWEEP_TPB), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
+    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB;
+    const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profile) {
         if (s->prof_used + 2 > s->prof_events.size()) {
@@ -355,8 +365,22 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         s->prof_used += 2;
         ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
     }
-    s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
-    ARMON_LAUNCH_CHECK(s->ctx);
+    if (s->use_ws) {
+        FixupArgs F;
+        F.count = s->fix_count + (s->sweep_index & 1);
+        F.count_next = s->fix_count + ((s->sweep_index + 1) & 1);
+        F.list = s->fix_list;
+        s->ws_kernel<<<grid, WS_TPB, 0, s->ctx->stream>>>(A, F);
+        ARMON_LAUNCH_CHECK(s->ctx);
+        if (s->fixup_kernel) {
+            s->fixup_kernel<<<2 * s->ctx->sm_count, 32, 0, s->ctx->stream>>>(A, F);
+            ARMON_LAUNCH_CHECK(s->ctx);
+        }
+        s->sweep_index++;
+    } else {
+        s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
+        ARMON_LAUNCH_CHECK(s->ctx);
+    }
     if (s->profile) ARMON_CUDA(cudaEventRecord(ev1, s->ctx->stream));
     s->sweep_launches++;
 
@@ -489,6 +513,37 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
         armon_set_error("no sweep kernel for this scheme combination");
         return ARMON_ERR_INVALID;
     }
+    // Kernel variant: the warp-specialised kernel pays off once the grid fills the GPU; tiny grids (the 100x100
+    // golden cases) are launch-bound and keep the single-role kernel.  ARMON_B200_KERNEL=single|ws overrides.
+    {
+        const char *env = getenv("ARMON_B200_KERNEL");
+        // measured at 8192^2 (profiles/): strict 3.25 ms (ws) vs 3.48 ms (single); fast 2.23 ms (ws) vs 1.88 ms (single)
+        const bool want_ws = env ? (std::string(env) == "ws") : (desc->kernel_variant == 2 ||
+                                   (desc->kernel_variant == 0 && desc->math_mode == ARMON_MATH_STRICT &&
+                                    D.nx * D.ny >= (1LL << 20)));
+        if (want_ws && desc->math_mode != ARMON_MATH_IEEE && !(env && std::string(env) == "single")) {
+            if (desc->math_mode == ARMON_MATH_STRICT) {
+                s->ws_kernel = biz ? sweep_ws_table_strict_biz(rl, desc->projection) : sweep_ws_table_strict_pg(rl, desc->projection);
+                s->fixup_kernel = biz ? sweep_fixup_table_biz(rl, desc->projection) : sweep_fixup_table_pg(rl, desc->projection);
+            } else {
+                s->ws_kernel = biz ? sweep_ws_table_fast_biz(rl, desc->projection) : sweep_ws_table_fast_pg(rl, desc->projection);
+            }
+            s->use_ws = s->ws_kernel != nullptr;
+        }
+        if (s->use_ws) {
+            // work list of the IEEE fix-up: one entry per (column, segment) at most
+            long long cap = 0;
+            for (int axis = 0; axis < 2; axis++) {
+                const long long nm = axis == ARMON_AXIS_X ? D.nx : D.ny, nw = axis == ARMON_AXIS_X ? D.ny : D.nx;
+                const long long seg = pick_segment(s, nm, nw);
+                const long long n = nw * ((nm + seg - 1) / seg);
+                cap = n > cap ? n : cap;
+            }
+            ARMON_CUDA(cudaMalloc(&s->fix_count, 2 * sizeof(unsigned)));
+            ARMON_CUDA(cudaMemsetAsync(s->fix_count, 0, 2 * sizeof(unsigned), ctx->stream));
+            ARMON_CUDA(cudaMalloc(&s->fix_list, (size_t)cap * sizeof(unsigned long long)));
+        }
+    }
     ARMON_CUDA(cudaMalloc(&s->ts, sizeof(DeviceTimeState)));
     ARMON_CUDA(cudaEventCreate(&s->ev_start));
     ARMON_CUDA(cudaEventCreate(&s->ev_stop));
@@ -504,6 +559,8 @@ int armon_solver_destroy(armon_solver *s)
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->ts) cudaFree(s->ts);
+    if (s->fix_count) cudaFree(s->fix_count);
+    if (s->fix_list) cudaFree(s->fix_list);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);

@@ -2,6 +2,7 @@
 // arithmetic mode x EOS so that they compile in parallel).
 #pragma once
 #include "sweep_kernel.cuh"
+#include "sweep_ws_kernel.cuh"
 
 typedef void (*sweep_fn_t)(const SweepArgs);
 
@@ -21,6 +22,42 @@ sweep_fn_t sweep_table_fast_biz(int rl, int proj);
             {sweep_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
+        };                                                                                  \
+        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
+        return table[rl][proj];                                                             \
+    }
+
+// Warp-specialised kernels (sweep_ws_kernel.cuh) and their IEEE fix-up kernels.
+typedef void (*sweep_ws_fn_t)(const SweepArgs, const FixupArgs);
+
+sweep_ws_fn_t sweep_ws_table_strict_pg(int rl, int proj);
+sweep_ws_fn_t sweep_ws_table_strict_biz(int rl, int proj);
+sweep_ws_fn_t sweep_ws_table_fast_pg(int rl, int proj);
+sweep_ws_fn_t sweep_ws_table_fast_biz(int rl, int proj);
+sweep_ws_fn_t sweep_fixup_table_pg(int rl, int proj);
+sweep_ws_fn_t sweep_fixup_table_biz(int rl, int proj);
+
+#define ARMON_DEFINE_WS_TABLE(NAME, R, DIV, EOS)                                             \
+    sweep_ws_fn_t NAME(int rl, int proj)                                                    \
+    {                                                                                       \
+        static const sweep_ws_fn_t table[4][2] = {                                          \
+            {sweep_ws_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_ws_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_ws_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_ws_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
+        };                                                                                  \
+        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
+        return table[rl][proj];                                                             \
+    }
+
+#define ARMON_DEFINE_FIXUP_TABLE(NAME, EOS)                                                  \
+    sweep_ws_fn_t NAME(int rl, int proj)                                                    \
+    {                                                                                       \
+        static const sweep_ws_fn_t table[4][2] = {                                          \
+            {sweep_fixup_kernel<sd, 0, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_fixup_kernel<sd, 1, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_fixup_kernel<sd, 2, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_fixup_kernel<sd, 3, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
         return table[rl][proj];                                                             \

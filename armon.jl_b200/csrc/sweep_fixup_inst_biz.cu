@@ -1,0 +1,3 @@
+// Instantiations of the IEEE fix-up kernel of the warp-specialised sweep, EOS ARMON_EOS_BIZARRIUM.
+#include "sweep_dispatch.h"
+ARMON_DEFINE_FIXUP_TABLE(sweep_fixup_table_biz, ARMON_EOS_BIZARRIUM)

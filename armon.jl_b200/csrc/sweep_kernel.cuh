@@ -61,16 +61,23 @@ __device__ __forceinline__ double flip_sign_by(double x, double src)
     return __longlong_as_double((long long)((unsigned long long)__double_as_longlong(x) ^ sb));
 }
 
-// src/projection_schemes.jl:15-20, with the multiplications by s = sign(d_p) done on the sign bit (exact)
+// src/projection_schemes.jl:15-20: s * max(0, min(s*d_p, s*d_m)) with s = sign(d_p).  The multiplications by
+// s in {-1, 0, +1} are exact sign manipulations, and max(0, min(.,.)) of two doubles whose first is >= 0 is an
+// unsigned comparison of the bit patterns: the whole limiter runs on the integer pipe (values identical to the
+// oracle's, including d_p == 0 -> 0).
 template <class R> __device__ __forceinline__ R slope_minmod_fused(R qm, R q0, R qp, R r_m, R r_p)
 {
     const R d_p = r_p * (qp - q0);
     const R d_m = r_m * (q0 - qm);
-    const double a = fabs(d_p.v);                      // s * d_p
-    const double b = flip_sign_by(d_m.v, d_p.v);       // s * d_m
-    const double m = fmax(0.0, fmin(a, b));
-    const double res = flip_sign_by(m, d_p.v);         // s * max(0, min(..))
-    return R(d_p.v == 0.0 ? 0.0 : res);
+    const unsigned sgn = (unsigned)__double2hiint(d_p.v) & 0x80000000u;
+    const unsigned a_hi = (unsigned)__double2hiint(d_p.v) & 0x7fffffffu, a_lo = (unsigned)__double2loint(d_p.v);   // |d_p|
+    const unsigned b_hi = (unsigned)__double2hiint(d_m.v) ^ sgn, b_lo = (unsigned)__double2loint(d_m.v);           // s*d_m
+    const bool b_neg = (int)b_hi < 0;                                   // min(a, b) < 0 (or -0): max(0, .) = 0
+    const bool b_lt_a = b_hi < a_hi || (b_hi == a_hi && b_lo < a_lo);   // both non-negative here
+    unsigned m_hi = b_lt_a ? b_hi : a_hi, m_lo = b_lt_a ? b_lo : a_lo;
+    m_hi = b_neg ? 0u : m_hi;
+    m_lo = b_neg ? 0u : m_lo;
+    return R(__hiloint2double((int)(m_hi | sgn), (int)m_lo));           // s * m
 }
 
 template <class R, int DIV, int EOS>

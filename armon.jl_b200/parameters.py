@@ -217,7 +217,7 @@ class ArmonParameters:
 
     # -- init_backend(params, ::B200Device; options...), src/parameters.jl:758-778 ----------------
     def _init_backend(self, math_mode="strict", march_segment=0, fused=True, device_id=None, bind_pcg=True,
-                      **options):
+                      kernel_variant="auto", **options):
         """Backend-specific options (like `armon_cpp_lib_src`/`use_md_iter` for Kokkos, ext/ArmonKokkos.jl:83-89).
 
         math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle (branch-free
@@ -236,6 +236,9 @@ class ArmonParameters:
         self.march_segment = int(march_segment)
         self.fused = bool(fused)
         self.bind_pcg = bool(bind_pcg)
+        if kernel_variant not in ("auto", "single", "ws"):
+            solver_error("config", f"unknown kernel_variant '{kernel_variant}'")
+        self.kernel_variant = kernel_variant   # "ws": warp-specialised producer/consumer sweep kernel
         self.device_id = int(os.environ.get("LOCAL_RANK", 0)) if device_id is None else int(device_id)
         self.backend_options = None   # set by BlockGrid / armon(): the library context
         return options

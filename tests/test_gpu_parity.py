@@ -92,9 +92,10 @@ def test_golden_vectors(test, fused, golden):
 
 
 # ---- 3. fused strict path == oracle, bit for bit --------------------------------------------------------
+@pytest.mark.parametrize("variant", ["single", "ws"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
-def test_fused_strict_bit_exact_on_golden_cases(test):
-    stats, grid = run_gpu(reference_params(test))
+def test_fused_strict_bit_exact_on_golden_cases(test, variant):
+    stats, grid = run_gpu(reference_params(test, kernel_variant=variant))
     orc = OracleSolver(reference_params(test), "strict", nthreads=1)
     _, dt, cycles, err = orc.time_loop()
     assert err == 0 and stats.cycles == cycles
@@ -117,11 +118,12 @@ VARIANTS = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["single", "ws"])
 @pytest.mark.parametrize("test,N,scheme,limiter,projection,splitting,cycles", VARIANTS)
-def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, splitting, cycles):
+def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, splitting, cycles, variant):
     kw = dict(N=N, scheme=scheme, riemann_limiter=limiter, projection=projection, axis_splitting=splitting,
               maxcycle=cycles)
-    stats, grid = run_gpu(reference_params(test, **kw))
+    stats, grid = run_gpu(reference_params(test, kernel_variant=variant, **kw))
     orc = OracleSolver(reference_params(test, **kw), "strict", nthreads=1)
     _, dt, ncyc, err = orc.time_loop()
     assert err == 0 and stats.cycles == ncyc == cycles
@@ -131,11 +133,12 @@ def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, s
     grid.close()
 
 
+@pytest.mark.parametrize("variant", ["single", "ws"])
 @pytest.mark.parametrize("seg", [8, 16, 40, 1000])
-def test_march_segment_does_not_change_results(seg):
+def test_march_segment_does_not_change_results(seg, variant):
     kw = dict(N=(90, 75), maxcycle=8)
-    _, g0 = run_gpu(reference_params("Sod_circ", **kw))
-    _, g1 = run_gpu(reference_params("Sod_circ", march_segment=seg, **kw))
+    _, g0 = run_gpu(reference_params("Sod_circ", kernel_variant="single", **kw))
+    _, g1 = run_gpu(reference_params("Sod_circ", march_segment=seg, kernel_variant=variant, **kw))
     for var in ("rho", "u", "v", "E"):
         assert_same(g1.real(var), g0.real(var), var)
     g0.close(); g1.close()
@@ -153,10 +156,11 @@ def test_cst_dt():
 
 
 # ---- 4. fast arithmetic mode: 1e-12 of field scale -------------------------------------------------------
+@pytest.mark.parametrize("variant", ["single", "ws"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
-def test_fused_fast_mode_within_tolerance(test, golden):
+def test_fused_fast_mode_within_tolerance(test, variant, golden):
     ref = golden(test)
-    stats, grid = run_gpu(reference_params(test, math_mode="fast"))
+    stats, grid = run_gpu(reference_params(test, math_mode="fast", kernel_variant=variant))
     orc = OracleSolver(reference_params(test), "strict", nthreads=1)
     orc.time_loop()
     assert stats.cycles == int(ref["cycles"]) == orc.state.cycle
@@ -165,6 +169,8 @@ def test_fused_fast_mode_within_tolerance(test, golden):
         assert scaled_max_diff(grid.real(var), orc.real(var)) <= 1e-12, var    # tolerance of north_star
     for var in ("rho", "u", "v", "p"):
         assert scaled_max_diff(grid.real(var), ref[var]) <= 1e-12, var
+        if test not in EXEMPT:     # the reference's own acceptance test (atol=1e-13, rtol=4eps, 0 differing cells)
+            assert count_differences(grid.real(var), ref[var]) == 0, var
     grid.close()
 
 
@@ -263,15 +269,17 @@ def test_strict_mode_handles_tiny_operands_like_ieee():
     kw = dict(N=(48, 40), maxcycle=4)
     scale = 1e-290
 
-    def run(mode):
-        params = reference_params("Sod_circ", math_mode=mode, **kw)
+    def run(mode, variant="single"):
+        params = reference_params("Sod_circ", math_mode=mode, kernel_variant=variant, **kw)
         grid = armon.BlockGrid(params)
         armon.init_test(params, grid)
         grid.set_array("rho", grid.host_array("rho") * scale)     # tiny densities: impedances ~1e-290 as divisors
         armon.time_loop(params, grid)
         return grid
 
-    g_strict, g_ieee = run("strict"), run("ieee")
+    g_strict, g_ws, g_ieee = run("strict"), run("strict", "ws"), run("ieee")
     for var in ("rho", "u", "v", "E"):
         assert_same(g_strict.real(var), g_ieee.real(var), var)
-    g_strict.close(); g_ieee.close()
+        assert_same(g_ws.real(var), g_ieee.real(var), var + " (ws + fix-up kernel)")
+    assert g_strict.time_state().current_dt == g_ieee.time_state().current_dt == g_ws.time_state().current_dt
+    g_strict.close(); g_ws.close(); g_ieee.close()
