@@ -214,6 +214,10 @@ struct armon_solver {
     // warp-specialised path (sweep_ws_kernel.cuh): main kernel + IEEE fix-up kernel (strict mode only)
     sweep_ws_fn_t     ws_kernel = nullptr, fixup_kernel = nullptr;
     bool              use_ws = false;
+    // TMA-staged marching kernel (sweep_tma_kernel.cuh); falls back to `kernel` per launch when the bulk-copy
+    // alignment rules do not hold (odd input pitch)
+    sweep_fn_t        tma_kernel = nullptr;
+    bool              use_tma = false;
     unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
     uint64_t          sweep_index = 0;
@@ -303,7 +307,7 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         return seg;
     }
     // as long as possible (8 warm-up rows per segment are redundant work) while keeping >= 6 waves of CTAs
-    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB, ctas_per_sm = s->use_ws ? 7 : 2;
+    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB, ctas_per_sm = s->use_ws ? 7 : 2;   // TMA_TPB == SWEEP_TPB
     const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
     const long long want = 6LL * ctas_per_sm * s->ctx->sm_count;
     const int cands[] = {512, 256, 128, 64, 32, 16};
@@ -377,6 +381,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
             ARMON_LAUNCH_CHECK(s->ctx);
         }
         s->sweep_index++;
+    } else if (s->use_tma && (A.pitch_in % 2) == 0) {
+        s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), s->ctx->stream>>>(A);
+        ARMON_LAUNCH_CHECK(s->ctx);
     } else {
         s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
@@ -518,9 +525,21 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     {
         const char *env = getenv("ARMON_B200_KERNEL");
         // measured at 8192^2 (profiles/): strict 3.25 ms (ws) vs 3.48 ms (single); fast 2.23 ms (ws) vs 1.88 ms (single)
-        const bool want_ws = env ? (std::string(env) == "ws") : (desc->kernel_variant == 2 ||
+        const bool want_tma = env ? (std::string(env) == "tma") : (desc->kernel_variant == 3);
+        if (want_tma && desc->math_mode != ARMON_MATH_IEEE) {
+            if (desc->math_mode == ARMON_MATH_STRICT)
+                s->tma_kernel = biz ? sweep_tma_table_strict_biz(rl, desc->projection) : sweep_tma_table_strict_pg(rl, desc->projection);
+            else
+                s->tma_kernel = biz ? sweep_tma_table_fast_biz(rl, desc->projection) : sweep_tma_table_fast_pg(rl, desc->projection);
+            if (s->tma_kernel) {
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)s->tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(TMA_TPB / 32 * sizeof(TmaWarpShared))));
+                s->use_tma = true;
+            }
+        }
+        const bool want_ws = !s->use_tma && (env ? (std::string(env) == "ws") : (desc->kernel_variant == 2 ||
                                    (desc->kernel_variant == 0 && desc->math_mode == ARMON_MATH_STRICT &&
-                                    D.nx * D.ny >= (1LL << 20)));
+                                    D.nx * D.ny >= (1LL << 20))));
         if (want_ws && desc->math_mode != ARMON_MATH_IEEE && !(env && std::string(env) == "single")) {
             if (desc->math_mode == ARMON_MATH_STRICT) {
                 s->ws_kernel = biz ? sweep_ws_table_strict_biz(rl, desc->projection) : sweep_ws_table_strict_pg(rl, desc->projection);

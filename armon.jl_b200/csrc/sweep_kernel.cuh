@@ -33,7 +33,7 @@
 
 constexpr int SWEEP_TPB = 128;      // threads per CTA = columns per CTA
 constexpr int SWEEP_CHUNK = 8;      // outputs between two flushes of the transposed staging buffer
-constexpr int SWEEP_STAGE_PITCH = SWEEP_CHUNK + 1;   // odd pitch: conflict-free 64-bit shared-memory writes
+constexpr int SWEEP_STAGE_PITCH = SWEEP_CHUNK + 2;   // rows stay 16-byte aligned for the 128-bit reads of flush_stage (2-way write conflicts)
 
 struct SweepArgs {
     const double *in[4];    // rho, ua, ut, E (ua: velocity along the march axis, ut: transverse velocity)
@@ -130,12 +130,13 @@ __device__ __forceinline__ void issue_loads(const SweepArgs &A, const SweepThrea
     for (int k = 0; k < 4; k++) v[k] = __ldg(T.base[k] + off);
 }
 
-// One march step: consumes cell a (already in `in`), emits cell a-4 when `emit`.  J = (a - a_begin) & 3 is static.
+// The arithmetic of one march step: consumes cell a (rho, ua, ut, E as read from memory), emits cell a-4 when `emit`.
+// J = (a - a_begin) & 3 is static.
 template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED, int J>
-__device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, Pipe<R> &P, double (&in)[4][4],
-                                           const long long a, const long long a_last, const R dt,
-                                           const typename Div<R, DIV>::Rcp &inv_dx, const bool emit,
-                                           const int k_chunk, const long long m1, double *stage)
+__device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T, Pipe<R> &P, R rho, R ua, R ut, R E,
+                                              const long long a, const R dt,
+                                              const typename Div<R, DIV>::Rcp &inv_dx, const bool emit,
+                                              const int k_chunk, const long long m1, double *stage)
 {
     typedef Div<R, DIV> D;
     constexpr int S0 = J & 3, S1 = (J + 3) & 3, S2 = (J + 2) & 3, S3 = (J + 1) & 3;
@@ -143,14 +144,8 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
     RangeFlag &f = T.flag;
 
     // ---- cell a: boundary factors, EOS (src/kernels.jl:4-55) ----
-    R rho(in[J][0]), ua(in[J][1]), ut(in[J][2]), E(in[J][3]);
     if (a < 0 && A.mirror_lo) { ua = ua * R(A.bc_a_lo); ut = ut * R(A.bc_t_lo); }
     else if (a >= A.nm && A.mirror_hi) { ua = ua * R(A.bc_a_hi); ut = ut * R(A.bc_t_hi); }
-    // prefetch the cell consumed 4 steps from now into the slot just freed
-    {
-        const long long an = a + 4 > a_last ? a_last : a + 4;
-        issue_loads(A, T, an, in[J]);
-    }
     const R c_out = P.cc[S0];   // c of cell a-4 (EOS at the start of this sweep), read before the slot is reused
     R p, c;
     eos_eval<R, DIV, EOS>(A, rho, ua, ut, E, p, c, f);
@@ -274,22 +269,56 @@ __device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, P
     P.Ar = Anr; P.Aru = Anru; P.Art = Anrt; P.ArE = AnrE;
 }
 
+// One march step of the register-prefetch variant: cell a is already in `in[J]`; the slot is refilled with the cell
+// consumed 4 steps from now.
+template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED, int J>
+__device__ __forceinline__ void march_step(const SweepArgs &A, SweepThread &T, Pipe<R> &P, double (&in)[4][4],
+                                           const long long a, const long long a_last, const R dt,
+                                           const typename Div<R, DIV>::Rcp &inv_dx, const bool emit,
+                                           const int k_chunk, const long long m1, double *stage)
+{
+    const R rho(in[J][0]), ua(in[J][1]), ut(in[J][2]), E(in[J][3]);
+    {
+        const long long an = a + 4 > a_last ? a_last : a + 4;
+        issue_loads(A, T, an, in[J]);
+    }
+    march_compute<R, DIV, RL, PROJ, EOS, STAGED, J>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, emit, k_chunk, m1, stage);
+}
+
 // Transposed store of one chunk: the warp's staging buffer holds, per variable, 32 columns x SWEEP_CHUNK march
-// cells; each column becomes a row of the transposed array, written as SWEEP_CHUNK contiguous doubles (4 rows
-// per warp store instruction).
+// cells; each column becomes a row of the transposed array, written as SWEEP_CHUNK contiguous doubles.
+// Fast path (full tile, even output pitch): 128-bit shared loads and global stores, 8 rows per warp instruction,
+// 16 store instructions per tile.  Ragged tiles (last columns / last chunk of a segment, odd pitch) take the
+// element-wise path.
 __device__ __forceinline__ void flush_stage(const SweepArgs &A, const double *stage, long long w0, long long mb, long long m1)
 {
     const int lane = threadIdx.x & 31;
-    const int rsub = lane / SWEEP_CHUNK, col = lane % SWEEP_CHUNK;
     __syncwarp();
+    if (w0 + 32 <= A.nw && mb + SWEEP_CHUNK <= m1 && !(A.pitch_out & 1)) {
+        const int r0 = lane >> 2, j = lane & 3;
+        const double2 *src = reinterpret_cast<const double2 *>(stage + r0 * SWEEP_STAGE_PITCH + 2 * j);
+        const long long off = (w0 + r0 + A.g) * A.pitch_out + (mb + A.g) + 2 * j;
+        const long long step = 8 * A.pitch_out;
+#pragma unroll 1
+        for (int v = 0; v < 4; v++) {
+            double *dst = A.out[v] + off;
 #pragma unroll
-    for (int v = 0; v < 4; v++) {
+            for (int it = 0; it < 4; it++) {
+                const double2 val = src[(v * 32 + it * 8) * SWEEP_STAGE_PITCH / 2];
+                *reinterpret_cast<double2 *>(dst + it * step) = val;
+            }
+        }
+    } else {
+        const int rsub = lane / SWEEP_CHUNK, col = lane % SWEEP_CHUNK;
 #pragma unroll
-        for (int it = 0; it < 32 / (32 / SWEEP_CHUNK); it++) {
-            const int r = it * (32 / SWEEP_CHUNK) + rsub;
-            const double val = stage[(v * 32 + r) * SWEEP_STAGE_PITCH + col];
-            const long long w = w0 + r, m = mb + col;
-            if (w < A.nw && m < m1) A.out[v][(w + A.g) * A.pitch_out + (m + A.g)] = val;
+        for (int v = 0; v < 4; v++) {
+#pragma unroll
+            for (int it = 0; it < 32 / (32 / SWEEP_CHUNK); it++) {
+                const int r = it * (32 / SWEEP_CHUNK) + rsub;
+                const double val = stage[(v * 32 + r) * SWEEP_STAGE_PITCH + col];
+                const long long w = w0 + r, m = mb + col;
+                if (w < A.nw && m < m1) A.out[v][(w + A.g) * A.pitch_out + (m + A.g)] = val;
+            }
         }
     }
     __syncwarp();
@@ -347,7 +376,7 @@ __device__ __forceinline__ void march_segment(const SweepArgs &A, SweepThread &T
 template <class R, int DIV, int RL, int PROJ, int EOS>
 __global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_BLOCKS) sweep_kernel(const SweepArgs A)
 {
-    __shared__ double stage_all[(SWEEP_TPB / 32) * 4 * 32 * SWEEP_STAGE_PITCH];
+    __shared__ __align__(16) double stage_all[(SWEEP_TPB / 32) * 4 * 32 * SWEEP_STAGE_PITCH];
     double *stage = stage_all + (threadIdx.x / 32) * (4 * 32 * SWEEP_STAGE_PITCH);
 
     const long long w = (long long)blockIdx.x * SWEEP_TPB + threadIdx.x;

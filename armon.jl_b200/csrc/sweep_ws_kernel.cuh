@@ -32,7 +32,7 @@ enum { WV_DISP = 0, WV_DXL = 1, WV_LR = 2, WV_LU = 3, WV_LT = 4, WV_LE = 5, WV_C
 
 struct WsShared {
     double ring[WS_NS][WS_NV][32];
-    double stage[4 * 32 * SWEEP_STAGE_PITCH];
+    __align__(16) double stage[4 * 32 * SWEEP_STAGE_PITCH];
     unsigned long long full[WS_NS], empty[WS_NS], fin;
     unsigned pflag[32];
 };

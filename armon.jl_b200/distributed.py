@@ -14,7 +14,7 @@ def is_initialized():
     return dist.is_available() and dist.is_initialized()
 
 
-def init_process_group(backend=None):
+def init_process_group(backend=None, timeout_s=None):
     """Rendezvous from the torchrun environment (RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT)."""
     import torch
     import torch.distributed as dist
@@ -25,6 +25,9 @@ def init_process_group(backend=None):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     kwargs = {}
+    if timeout_s is not None:
+        import datetime
+        kwargs["timeout"] = datetime.timedelta(seconds=float(timeout_s))
     if backend == "nccl":
         local = int(os.environ.get("LOCAL_RANK", 0))
         torch.cuda.set_device(local)

@@ -179,8 +179,12 @@ def run_cpu(args):
     dist.destroy_process_group()
 
 
+def log(*a):
+    print(f"[rank {os.environ.get('RANK', '?')}]", *a, file=sys.stderr, flush=True)
+
+
 def run_gpu(args):
-    rank, world = adist.init_process_group("nccl")
+    rank, world = adist.init_process_group("nccl", timeout_s=90)
     assert world == args.world
     grids = [(1, world), (world, 1)] + ([(2, world // 2)] if world >= 4 and world % 2 == 0 else [])
     cases = [("Sod_circ", (192, 160), 12, "strict", "Sequential"), ("Sedov", (128, 128), 10, "strict", "Godunov"),
@@ -191,6 +195,7 @@ def run_gpu(args):
         kw = dict(test=test, N=global_n, maxcycle=cycles, math_mode=math, axis_splitting=splitting,
                   return_data=True, **SCHEME)
         ref = None
+        log("case", test, global_n, math, splitting)
         if rank == 0:
             stats = armon.armon(armon.ArmonParameters(**kw))
             ref = {v: stats.data.real(v).copy() for v in ("rho", "u", "v", "E", "p")}
@@ -200,7 +205,9 @@ def run_gpu(args):
         for P in grids:
             params = armon.ArmonParameters(use_MPI=True, P=P, rank=rank, proc_size=world, **kw)
             check_decomposition(params, global_n, P, rank)
+            log("  P", P, "running")
             stats = armon.armon(params)
+            log("  P", P, "done", stats.cycles, stats.last_dt)
             for v in ("rho", "u", "v", "E", "p"):
                 glob = gather_global(stats.data.real(v), params, P, global_n)
                 if rank == 0:
@@ -217,6 +224,7 @@ def run_gpu(args):
     for P in grids:
         params = armon.ArmonParameters(test="Sod", N=(64, 48), use_MPI=True, P=P, rank=rank, proc_size=world,
                                        return_data=True, **SCHEME)
+        log("halo test P", P)
         grid = armon.BlockGrid(params)
         armon.init_test(params, grid)
         g, (nx, ny) = params.nghost, params.N
