@@ -120,6 +120,32 @@ __global__ void k_init_dt(long long n_rows, long long n_cols, long long pitch, i
     }
 }
 
+// boundary_conditions! (src/halo_exchange.jl:2-36) for the two sides along the march axis of the sweep about to run:
+// ghost row -1-k <- real row k (low side), ghost row nm+k <- real row nm-1-k (high side), k = 0..g-1, real columns
+// only (no corners, src/blocking/blocking.jl:148-172); rho and E copied, the velocities multiplied by the factors of
+// boundary_condition(test, side) (src/tests.jl:150-211).  O(perimeter); the marching kernels then read every ghost
+// row as plain data, whether it came from here or from the halo exchange.
+struct BcFillArgs {
+    double *rho, *ua, *ut, *E;
+    long long nm, nw, pitch;
+    int g, lo, hi;
+    double fa_lo, ft_lo, fa_hi, ft_hi;
+};
+
+__global__ void k_bc_fill(BcFillArgs B)
+{
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y, side = blockIdx.z;
+    if (w >= B.nw || !(side == 0 ? B.lo : B.hi)) return;
+    const long long src_row = side == 0 ? k : B.nm - 1 - k, dst_row = side == 0 ? -1 - k : B.nm + k;
+    const long long is = (src_row + B.g) * B.pitch + w + B.g, id = (dst_row + B.g) * B.pitch + w + B.g;
+    const double fa = side == 0 ? B.fa_lo : B.fa_hi, ft = side == 0 ? B.ft_lo : B.ft_hi;
+    B.rho[id] = B.rho[is];
+    B.E[id] = B.E[is];
+    B.ua[id] = __dmul_rn(B.ua[is], fa);
+    B.ut[id] = __dmul_rn(B.ut[is], ft);
+}
+
 // ---- layout helpers ---------------------------------------------------------------------------------------------
 struct Ptr4 { const double *in[4]; double *out[4]; };
 
@@ -218,6 +244,9 @@ struct armon_solver {
     // alignment rules do not hold (odd input pitch)
     sweep_fn_t        tma_kernel = nullptr;
     bool              use_tma = false;
+    // cp.async-staged marching kernel (sweep_async_kernel.cuh)
+    sweep_fn_t        async_kernel = nullptr;
+    bool              use_async = false;
     unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
     uint64_t          sweep_index = 0;
@@ -353,6 +382,17 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     A.ts = s->ts;
     A.acc_slot = last_of_cycle ? 0 : 1;
 
+    if (A.mirror_lo || A.mirror_hi) {
+        BcFillArgs B;
+        B.rho = const_cast<double *>(A.in[0]); B.ua = const_cast<double *>(A.in[1]);
+        B.ut = const_cast<double *>(A.in[2]); B.E = const_cast<double *>(A.in[3]);
+        B.nm = A.nm; B.nw = A.nw; B.pitch = A.pitch_in; B.g = A.g; B.lo = A.mirror_lo; B.hi = A.mirror_hi;
+        B.fa_lo = A.bc_a_lo; B.ft_lo = A.bc_t_lo; B.fa_hi = A.bc_a_hi; B.ft_hi = A.bc_t_hi;
+        const dim3 bgrid((unsigned)((A.nw + TPB - 1) / TPB), (unsigned)A.g, 2);
+        k_bc_fill<<<bgrid, TPB, 0, s->ctx->stream>>>(B);
+        ARMON_LAUNCH_CHECK(s->ctx);
+    }
+
     const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB;
     const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -381,6 +421,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
             ARMON_LAUNCH_CHECK(s->ctx);
         }
         s->sweep_index++;
+    } else if (s->use_async) {
+        s->async_kernel<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(AsyncWarpShared), s->ctx->stream>>>(A);
+        ARMON_LAUNCH_CHECK(s->ctx);
     } else if (s->use_tma && (A.pitch_in % 2) == 0) {
         s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
@@ -525,6 +568,8 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     {
         const char *env = getenv("ARMON_B200_KERNEL");
         // measured at 8192^2 (profiles/): strict 3.25 ms (ws) vs 3.48 ms (single); fast 2.23 ms (ws) vs 1.88 ms (single)
+        // kernel_variant / ARMON_B200_KERNEL: 0 auto (= cp.async-staged), 1 single (register prefetch), 2 ws, 3 tma, 4 async.
+        // Measured at 8192^2, fast mode (profiles/): async 1.18 ms, tma 1.55 ms, single 1.68 ms, ws 2.2 ms per sweep.
         const bool want_tma = env ? (std::string(env) == "tma") : (desc->kernel_variant == 3);
         if (want_tma && desc->math_mode != ARMON_MATH_IEEE) {
             if (desc->math_mode == ARMON_MATH_STRICT)
@@ -537,9 +582,20 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                 s->use_tma = true;
             }
         }
-        const bool want_ws = !s->use_tma && (env ? (std::string(env) == "ws") : (desc->kernel_variant == 2 ||
-                                   (desc->kernel_variant == 0 && desc->math_mode == ARMON_MATH_STRICT &&
-                                    D.nx * D.ny >= (1LL << 20))));
+        const bool want_async = !s->use_tma && (env ? (std::string(env) == "async" || std::string(env) == "auto")
+                                                    : (desc->kernel_variant == 4 || desc->kernel_variant == 0));
+        if (want_async && desc->math_mode != ARMON_MATH_IEEE) {
+            if (desc->math_mode == ARMON_MATH_STRICT)
+                s->async_kernel = biz ? sweep_async_table_strict_biz(rl, desc->projection) : sweep_async_table_strict_pg(rl, desc->projection);
+            else
+                s->async_kernel = biz ? sweep_async_table_fast_biz(rl, desc->projection) : sweep_async_table_fast_pg(rl, desc->projection);
+            if (s->async_kernel) {
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared))));
+                s->use_async = true;
+            }
+        }
+        const bool want_ws = !s->use_tma && !s->use_async && (env ? (std::string(env) == "ws") : (desc->kernel_variant == 2));
         if (want_ws && desc->math_mode != ARMON_MATH_IEEE && !(env && std::string(env) == "single")) {
             if (desc->math_mode == ARMON_MATH_STRICT) {
                 s->ws_kernel = biz ? sweep_ws_table_strict_biz(rl, desc->projection) : sweep_ws_table_strict_pg(rl, desc->projection);

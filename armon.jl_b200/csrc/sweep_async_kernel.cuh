@@ -1,0 +1,168 @@
+// sweep_async_kernel.cuh -- the fused axis-sweep marching kernel with inputs staged through shared memory by
+// per-thread asynchronous copies (cp.async, LDGSTS).
+//
+// Same mathematics, data layout and HBM traffic as sweep_kernel.cuh (read it first; march_compute is shared).  The
+// register-prefetch kernel keeps the 4 rows in flight in 32 registers and the round-1 profile shows 15 % of its cycles
+// waiting on those loads (HBM latency under load exceeds a 4-row lead); the bulk-copy (TMA) variant of
+// sweep_tma_kernel.cuh removes the wait but pays ~45 issue slots per step for the elected-lane producer code.  Here
+// every thread copies its own 8 bytes of rho, ua, ut, E of the row ASYNC_NS - 1 steps ahead into a per-warp ring
+// [slot][variable][lane] with four `cp.async` instructions and one commit per step; the consumer side is one
+// `cp.async.wait_group` and four conflict-free 8-byte shared loads.  A thread only ever reads what it copied itself:
+// no barrier of any kind inside the march, no alignment requirement beyond 8 bytes (any pitch works), and the lead is
+// a compile-time constant that costs shared memory instead of registers.
+#pragma once
+
+#include "sweep_kernel.cuh"
+
+#ifndef ASYNC_NS
+#define ASYNC_NS 8          // ring slots per warp; rows in flight = ASYNC_NS - 1
+#endif
+constexpr int ASYNC_TPB = 128;
+
+struct AsyncWarpShared {
+    double ring[ASYNC_NS][4][32];                          // [slot][variable][lane]
+    double stage[4 * 32 * SWEEP_STAGE_PITCH];              // transposed-store staging (flush_stage)
+};
+
+__device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copies of the thread's cell of the array row whose first cell has element offset `off` into ring slot `s`
+__device__ __forceinline__ void async_issue_row(const SweepThread &T, unsigned ring_lane, long long off, int s)
+{
+    const unsigned dst = ring_lane + 1024u * (unsigned)s;
+#pragma unroll
+    for (int k = 0; k < 4; k++) async_copy8(dst + 256u * k, T.base[k] + off);
+}
+
+#ifndef ASYNC_MIN_BLOCKS
+#define ASYNC_MIN_BLOCKS 2
+#endif
+
+template <class R, int DIV, int RL, int PROJ, int EOS>
+__global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kernel(const SweepArgs A)
+{
+    extern __shared__ __align__(128) unsigned char async_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AsyncWarpShared &S = reinterpret_cast<AsyncWarpShared *>(async_smem_raw)[warp];
+
+    const long long w = (long long)blockIdx.x * ASYNC_TPB + threadIdx.x;
+    const long long w0 = (long long)blockIdx.x * ASYNC_TPB + (threadIdx.x & ~31);
+    const long long m0 = (long long)blockIdx.y * A.seg;
+    const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
+
+    SweepThread T;
+    T.valid = w < A.nw;
+    T.col = (T.valid ? w : A.nw - 1) + A.g;
+#pragma unroll
+    for (int k = 0; k < 4; k++) T.base[k] = A.in[k] + T.col;
+    T.amax = 0ULL; T.tmax = 0ULL;
+
+    const DeviceTimeState *ts = A.ts;
+    if (ts->done) {   // see sweep_kernel: copy the state through so that the host's buffer rotation stays valid
+        if (T.valid) {
+            for (long long m = m0; m < m1; m++) {
+                const long long i = (m + A.g) * A.pitch_in + T.col;
+                const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
+#pragma unroll
+                for (int k = 0; k < 4; k++) A.out[k][o] = A.in[k][i];
+            }
+        }
+        return;
+    }
+    if (w0 >= A.nw) return;   // warp entirely outside the domain (warps are independent: no CTA barrier below)
+
+    const R dt = R(ts->current_dt) * R(A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
+    const long long nchunks = (m1 - m0 + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
+    const long long a_begin = m0 - 4;
+    const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed
+
+    // prologue: rows a_begin .. a_begin + ASYNC_NS - 2, one commit group per row (a segment has >= 16 steps);
+    // afterwards step t fetches row a_begin + t + ASYNC_NS - 1 into the slot consumed at step t - 1
+    static_assert(ASYNC_NS >= 2 && ASYNC_NS <= 16 && (ASYNC_NS & (ASYNC_NS - 1)) == 0, "ring size");
+    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(&S.ring[0][0][lane]);
+#pragma unroll 1
+    for (int s = 0; s < ASYNC_NS - 1; s++) {
+        async_issue_row(T, ring_lane, march_row_offset(A, a_begin + s), s);
+        async_commit();
+    }
+    long long off_run = march_row_offset(A, a_begin + ASYNC_NS - 1);   // offset of row a + ASYNC_NS - 1
+    const long long off_max = (A.nm + 2 * A.g - 1) * A.pitch_in;
+
+    const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
+    Pipe<R> P;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.); P.cut[j] = R(0.); P.cE[j] = R(1.); P.cc[j] = R(1.);
+        P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
+        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
+        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
+    }
+    P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
+    P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
+
+    double *stage = S.stage;
+    long long a = a_begin;
+    const long long n_iter = 2 + 2 * nchunks;
+    unsigned step = 0;   // a - a_begin
+
+    // Group accounting: ASYNC_NS - 1 groups before the loop, exactly one per step (possibly empty) afterwards, so the
+    // group of the row consumed at step t is complete once at most ASYNC_NS - 2 groups are pending.
+#define ASYNC_STEP(J)                                                                                       \
+    {                                                                                                       \
+        async_wait<ASYNC_NS - 2>();                                                                         \
+        const double *slot = &S.ring[step & (ASYNC_NS - 1)][0][lane];                                       \
+        const R rho(slot[0]), ua(slot[32]), ut(slot[64]), E(slot[96]);                                      \
+        {                                                                                                   \
+            const long long an = a + (ASYNC_NS - 1);                                                        \
+            if (an <= a_last)                                                                               \
+                async_issue_row(T, ring_lane, off_run, (int)((step + ASYNC_NS - 1) & (ASYNC_NS - 1)));      \
+            async_commit();                                                                                 \
+            if (off_run < off_max) off_run += A.pitch_in;   /* clamped at the last array row */             \
+        }                                                                                                   \
+        march_compute<R, DIV, RL, PROJ, EOS, true, J>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, emit, kc + J, m1, stage); \
+        a++; step++;                                                                                        \
+    }
+
+#pragma unroll 1
+    for (long long it = 0; it < n_iter; it++) {
+        const bool emit = it >= 2;
+        const int kc = (int)(it & 1) * 4;
+        ASYNC_STEP(0)
+        ASYNC_STEP(1)
+        ASYNC_STEP(2)
+        ASYNC_STEP(3)
+        if (A.transpose_out && emit && (it & 1)) flush_stage(A, stage, w0, a - 12, m1);
+    }
+#undef ASYNC_STEP
+    async_wait<0>();
+
+    if (DIV == DIV_FLAGGED) {
+        // see sweep_kernel: threads whose operands left the proven range of the branch-free division recompute
+        // their segment with nvcc's full IEEE division (register-prefetch path, direct stores)
+        range_check_dividend(dt.v, T.flag);
+        if (T.flag.bad() && T.valid) {
+            T.amax = 0ULL; T.tmax = 0ULL;
+            march_segment<R, DIV_IEEE, RL, PROJ, EOS, false>(A, T, dt, m0, m1, w0, stage);
+            if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(&A.ts->redo_count, 1u);
+        }
+        __syncwarp();
+    }
+
+    unsigned long long am = T.amax, tm = T.tmax;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);
+        const unsigned long long ot = __shfl_xor_sync(0xffffffffu, tm, off);
+        am = oa > am ? oa : am;
+        tm = ot > tm ? ot : tm;
+    }
+    if (lane == 0) {
+        atomicMax(&A.ts->acc[A.acc_slot][0], am);
+        atomicMax(&A.ts->acc[A.acc_slot][1], tm);
+    }
+}

@@ -4,6 +4,7 @@
 #include "sweep_kernel.cuh"
 #include "sweep_ws_kernel.cuh"
 #include "sweep_tma_kernel.cuh"
+#include "sweep_async_kernel.cuh"
 
 typedef void (*sweep_fn_t)(const SweepArgs);
 
@@ -78,6 +79,25 @@ sweep_fn_t sweep_tma_table_fast_biz(int rl, int proj);
             {sweep_tma_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_tma_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_tma_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
+        };                                                                                  \
+        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
+        return table[rl][proj];                                                             \
+    }
+
+// cp.async-staged marching kernels (sweep_async_kernel.cuh); same signature as the register-prefetch kernels.
+sweep_fn_t sweep_async_table_strict_pg(int rl, int proj);
+sweep_fn_t sweep_async_table_strict_biz(int rl, int proj);
+sweep_fn_t sweep_async_table_fast_pg(int rl, int proj);
+sweep_fn_t sweep_async_table_fast_biz(int rl, int proj);
+
+#define ARMON_DEFINE_ASYNC_TABLE(NAME, R, DIV, EOS)                                          \
+    sweep_fn_t NAME(int rl, int proj)                                                       \
+    {                                                                                       \
+        static const sweep_fn_t table[4][2] = {                                             \
+            {sweep_async_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_async_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_async_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
+            {sweep_async_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
         return table[rl][proj];                                                             \

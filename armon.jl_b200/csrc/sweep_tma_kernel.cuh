@@ -4,11 +4,10 @@
 // changes is how the cells of the march reach the threads: instead of per-thread 8-byte loads prefetched 4 rows
 // ahead in registers (32 registers, and a prefetch distance the compiler shortens under register pressure -- the
 // round-1 profile shows 15 % of the cycles waiting on those loads), every warp owns a shared-memory ring of
-// TMA_NS array rows.  Four lanes of the warp each issue one bulk asynchronous copy (cp.async.bulk, the 1-D TMA
-// path: 32 columns x 8 bytes = 256 contiguous bytes of one variable) per row, TMA_NS rows ahead of the march, and
+// TMA_NS array rows.  One lane of the warp issues four bulk asynchronous copies (cp.async.bulk, the 1-D TMA path:
+// 32 columns x 8 bytes = 256 contiguous bytes of one variable) per row, TMA_NS - 1 rows ahead of the march, and
 // the copies signal a per-slot mbarrier with their byte count.  The consumer side is one mbarrier wait and four
-// conflict-free 8-byte shared loads per step.  Mirrored rows at global edges (boundary_conditions!,
-// src/halo_exchange.jl:2-36) are just a different source row for the copy.
+// conflict-free 8-byte shared loads per step.
 //
 // Requirements of the bulk copy (16-byte aligned source, size multiple of 16): even input pitch and 16-byte aligned
 // arrays; the host falls back to sweep_kernel otherwise.  Warps are independent (no CTA-wide barrier in the march).
@@ -58,25 +57,24 @@ __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void *src, unsi
                  : "memory");
 }
 
-// Per-warp producer state: lanes 0..3 copy variable `lane` of one array row into the ring.
+// Per-warp producer state (warp-uniform).
 struct TmaProducer {
-    const double *src;     // A.in[lane & 3] + w0 + g
-    unsigned dst;          // shared address of ring[0][lane & 3][0]
+    unsigned ring;         // shared address of ring[0][0][0]
     unsigned bar;          // shared address of full[0]
     unsigned bytes;        // bytes per variable and row (<= 256, multiple of 16)
+    long long col0;        // w0 + g: first column of the warp inside an array row
 };
 
-// Issue the copies of array row `a` (march index, mirrored / clamped like march_row_offset) into slot `s`.
-// Called by the whole warp after the slot was consumed (the __syncwarp orders the generic-proxy reads of all lanes
-// before the async-proxy writes issued below).
-__device__ __forceinline__ void tma_issue_row(const SweepArgs &A, const TmaProducer &Q, long long a, int s, int lane)
+// One lane issues the four bulk copies (rho, ua, ut, E) of the array row whose first cell has element offset `off`
+// (march_row_offset: mirrored / clamped at the edges) into slot `s`; the copies complete on the slot's mbarrier.
+__device__ __forceinline__ void tma_issue_row(const SweepArgs &A, const TmaProducer &Q, long long off, int s, int lane)
 {
-    __syncwarp();
-    if (lane < 4) {
-        const long long off = march_row_offset(A, a);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) tma_mbar_expect_tx(Q.bar + 8u * s, 4u * Q.bytes);
-        tma_bulk_g2s(Q.dst + (unsigned)(s * 4 * 32 * 8), Q.src + off, Q.bytes, Q.bar + 8u * s);
+    if (lane == 0) {
+        const unsigned bar = Q.bar + 8u * (unsigned)s, dst = Q.ring + 1024u * (unsigned)s;
+        tma_mbar_expect_tx(bar, 4u * Q.bytes);
+        const long long o = off + Q.col0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_bulk_g2s(dst + 256u * k, A.in[k] + o, Q.bytes, bar);
     }
 }
 
@@ -132,19 +130,20 @@ __global__ void __launch_bounds__(TMA_TPB, TMA_MIN_BLOCKS) sweep_tma_kernel(cons
     const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed
 
     TmaProducer Q;
+    Q.ring = tma_smem_u32(&S.ring[0][0][0]);
+    Q.bar = tma_smem_u32(&S.full[0]);
+    Q.col0 = w0 + A.g;
     {
-        const int k = lane & 3;
-        const double *base = k == 0 ? A.in[0] : (k == 1 ? A.in[1] : (k == 2 ? A.in[2] : A.in[3]));
-        Q.src = base + w0 + A.g;
-        Q.dst = tma_smem_u32(&S.ring[0][k][0]);
-        Q.bar = tma_smem_u32(&S.full[0]);
         const long long cols = A.nw - w0 < 32 ? A.nw - w0 : 32;
         Q.bytes = (unsigned)(cols * 8);
     }
-    // prologue: fill the ring (a segment has at least 16 >= TMA_NS steps)
+    // prologue: rows a_begin .. a_begin + TMA_NS - 2 (a segment has at least 16 >= TMA_NS steps); afterwards step t
+    // fetches row a_begin + t + TMA_NS - 1 into the slot consumed at step t - 1
     static_assert(TMA_NS <= 16 && (TMA_NS & (TMA_NS - 1)) == 0, "ring size");
 #pragma unroll 1
-    for (int s = 0; s < TMA_NS; s++) tma_issue_row(A, Q, a_begin + s, s, lane);
+    for (int s = 0; s < TMA_NS - 1; s++) tma_issue_row(A, Q, march_row_offset(A, a_begin + s), s, lane);
+    long long off_run = march_row_offset(A, a_begin + TMA_NS - 1);   // offset of row a + TMA_NS - 1
+    const long long off_max = (A.nm + 2 * A.g - 1) * A.pitch_in;
 
     const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
     Pipe<R> P;
@@ -156,6 +155,7 @@ __global__ void __launch_bounds__(TMA_TPB, TMA_MIN_BLOCKS) sweep_tma_kernel(cons
         P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
     }
     P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
+    P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
 
     double *stage = S.stage;
     long long a = a_begin;
@@ -168,8 +168,13 @@ __global__ void __launch_bounds__(TMA_TPB, TMA_MIN_BLOCKS) sweep_tma_kernel(cons
         tma_mbar_wait(Q.bar + 8u * s, (step / TMA_NS) & 1u);                                                \
         const double *slot = &S.ring[s][0][lane];                                                           \
         const R rho(slot[0]), ua(slot[32]), ut(slot[64]), E(slot[96]);                                      \
-        /* refill the slot; never issue a copy that would not be consumed (none may be in flight at exit) */ \
-        if (a + TMA_NS <= a_last) tma_issue_row(A, Q, a + TMA_NS, s, lane);                                 \
+        __syncwarp();                                                                                       \
+        {   /* refill the slot consumed at the previous step; never issue a copy that would not be consumed */ \
+            const long long an = a + (TMA_NS - 1);                                                          \
+            if (an <= a_last)                                                                               \
+                tma_issue_row(A, Q, off_run, (int)((step + TMA_NS - 1) & (TMA_NS - 1)), lane);              \
+            if (off_run < off_max) off_run += A.pitch_in;   /* clamped at the last array row */             \
+        }                                                                                                   \
         march_compute<R, DIV, RL, PROJ, EOS, true, J>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, emit, kc + J, m1, stage); \
         a++; step++;                                                                                        \
     }

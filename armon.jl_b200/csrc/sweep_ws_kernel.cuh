@@ -81,8 +81,6 @@ __device__ __forceinline__ void ws_producer_step(const SweepArgs &A, SweepThread
     const int lane = threadIdx.x & 31;
 
     R rho(in[J][0]), ua(in[J][1]), ut(in[J][2]), E(in[J][3]);
-    if (a < 0 && A.mirror_lo) { ua = ua * R(A.bc_a_lo); ut = ut * R(A.bc_t_lo); }
-    else if (a >= A.nm && A.mirror_hi) { ua = ua * R(A.bc_a_hi); ut = ut * R(A.bc_t_hi); }
     {
         const long long an = a + 4 > a_last ? a_last : a + 4;
         issue_loads(A, T, an, in[J]);
