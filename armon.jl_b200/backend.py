@@ -227,6 +227,12 @@ class B200Device:
         check(self.lib.armon_ctx_comm_init(self._ctx, buf, int(rank), int(nranks)), "armon_ctx_comm_init")
         self.rank, self.nranks = int(rank), int(nranks)
 
+    def comm_destroy(self):
+        """Collective teardown of the communicator: every rank must call it at the same point of the program."""
+        if self.nranks > 1:
+            check(self.lib.armon_ctx_comm_destroy(self._ctx), "armon_ctx_comm_destroy")
+            self.rank, self.nranks = 0, 1
+
     def unique_id(self):
         buf = (C.c_char * 128)()
         check(self.lib.armon_comm_unique_id(buf), "armon_comm_unique_id")

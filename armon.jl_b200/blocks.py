@@ -91,9 +91,11 @@ class BlockGrid:
         self.params = params
         self.device = device or params.backend_options or B200Device(params.device_id)
         params.backend_options = self.device
+        self._owns_comm = False
         if params.use_MPI and params.proc_size > 1 and self.device.nranks == 1:
             from .distributed import setup_device_comm
             setup_device_comm(params, self.device)
+            self._owns_comm = True
         self.lib = self.device.lib
         nx, ny = params.N
         g = params.nghost
@@ -144,9 +146,14 @@ class BlockGrid:
         return st
 
     def close(self):
+        """Release the solver and, for a multi-rank grid, the NCCL communicator.  Collective when `use_MPI`: every
+        rank must call it at the same point (the communicator teardown waits for the peers)."""
         if self._solver is not None:
             self._solver_finalizer()
             self._solver = None
+        if self._owns_comm:
+            self.device.comm_destroy()
+            self._owns_comm = False
 
     # -- host <-> device -----------------------------------------------------------------------------------
     def device_to_host(self, vars=MAIN_VARS):       # device_to_host!, src/blocking/blocks.jl:121-143

@@ -77,7 +77,10 @@ int armon_ctx_destroy(armon_ctx *ctx)
 {
     if (!ctx) return ARMON_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    // ncclCommDestroy is collective in effect (it waits for the peers' proxies to disconnect): it belongs to
+    // armon_ctx_comm_destroy, which every rank calls at the same point of the program.  A context dropped with a live
+    // communicator (garbage collection, error paths: not synchronised across ranks) aborts it instead of blocking.
+    if (ctx->comm) { ncclCommAbort(ctx->comm); ctx->comm = nullptr; }
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -198,6 +201,8 @@ int armon_ctx_comm_destroy(armon_ctx *ctx)
         ARMON_CUDA(cudaStreamSynchronize(ctx->stream));
         ARMON_NCCL(ncclCommDestroy(ctx->comm));
         ctx->comm = nullptr;
+        ctx->rank = 0;
+        ctx->nranks = 1;
     }
     return ARMON_OK;
 }

@@ -253,7 +253,8 @@ int armon_selftest_math(armon_ctx *ctx, uint64_t seed, uint64_t n_samples, uint6
  * ------------------------------------------------------------------------------------------------- */
 int armon_comm_unique_id(char id[128]);                                   /* ncclGetUniqueId on rank 0 */
 int armon_ctx_comm_init(armon_ctx *ctx, const char id[128], int rank, int nranks);   /* ncclCommInitRank */
-int armon_ctx_comm_destroy(armon_ctx *ctx);
+int armon_ctx_comm_destroy(armon_ctx *ctx);   /* ncclCommDestroy: collective in effect, every rank calls it at the same
+                                                  point; armon_ctx_destroy on a live communicator aborts it instead */
 
 #ifdef __cplusplus
 }
