@@ -245,7 +245,7 @@ struct armon_solver {
     sweep_fn_t        tma_kernel = nullptr;
     bool              use_tma = false;
     // cp.async-staged marching kernel (sweep_async_kernel.cuh)
-    sweep_fn_t        async_kernel = nullptr;
+    sweep_fn_t        async_kernel[2] = {nullptr, nullptr};   // [transposed output]
     bool              use_async = false;
     unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
@@ -422,7 +422,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         }
         s->sweep_index++;
     } else if (s->use_async) {
-        s->async_kernel<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(AsyncWarpShared), s->ctx->stream>>>(A);
+        s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(AsyncWarpShared), s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
     } else if (s->use_tma && (A.pitch_in % 2) == 0) {
         s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), s->ctx->stream>>>(A);
@@ -585,15 +585,21 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
         const bool want_async = !s->use_tma && (env ? (std::string(env) == "async" || std::string(env) == "auto")
                                                     : (desc->kernel_variant == 4 || desc->kernel_variant == 0));
         if (want_async && desc->math_mode != ARMON_MATH_IEEE) {
-            if (desc->math_mode == ARMON_MATH_STRICT)
-                s->async_kernel = biz ? sweep_async_table_strict_biz(rl, desc->projection) : sweep_async_table_strict_pg(rl, desc->projection);
-            else
-                s->async_kernel = biz ? sweep_async_table_fast_biz(rl, desc->projection) : sweep_async_table_fast_pg(rl, desc->projection);
-            if (s->async_kernel) {
-                ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared))));
-                s->use_async = true;
+            bool ok = true;
+            for (int tr = 0; tr < 2; tr++) {
+                if (desc->math_mode == ARMON_MATH_STRICT)
+                    s->async_kernel[tr] = biz ? sweep_async_table_strict_biz(rl, desc->projection, tr)
+                                              : sweep_async_table_strict_pg(rl, desc->projection, tr);
+                else
+                    s->async_kernel[tr] = biz ? sweep_async_table_fast_biz(rl, desc->projection, tr)
+                                              : sweep_async_table_fast_pg(rl, desc->projection, tr);
+                ok = ok && s->async_kernel[tr] != nullptr;
+                if (s->async_kernel[tr])
+                    ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel[tr],
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared))));
             }
+            s->use_async = ok;
         }
         const bool want_ws = !s->use_tma && !s->use_async && (env ? (std::string(env) == "ws") : (desc->kernel_variant == 2));
         if (want_ws && desc->math_mode != ARMON_MATH_IEEE && !(env && std::string(env) == "single")) {

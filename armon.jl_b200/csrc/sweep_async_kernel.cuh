@@ -43,7 +43,9 @@ __device__ __forceinline__ void async_issue_row(const SweepThread &T, unsigned r
 #define ASYNC_MIN_BLOCKS 2
 #endif
 
-template <class R, int DIV, int RL, int PROJ, int EOS>
+// TR: 1 = the output is written transposed (through the staging tile), 0 = in the layout it was read (A.transpose_out
+// must agree).
+template <class R, int DIV, int RL, int PROJ, int EOS, int TR>
 __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kernel(const SweepArgs A)
 {
     extern __shared__ __align__(128) unsigned char async_smem_raw[];
@@ -107,36 +109,44 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
 
     double *stage = S.stage;
     long long a = a_begin;
-    const long long n_iter = 2 + 2 * nchunks;
     unsigned step = 0;   // a - a_begin
 
-    // Group accounting: ASYNC_NS - 1 groups before the loop, exactly one per step (possibly empty) afterwards, so the
-    // group of the row consumed at step t is complete once at most ASYNC_NS - 2 groups are pending.
-#define ASYNC_STEP(J)                                                                                       \
+    // Group accounting: ASYNC_NS - 1 groups before the loop, exactly one per step afterwards, so the group of the row
+    // consumed at step t is complete once at most ASYNC_NS - 2 groups are pending.  Rows past the end of the segment
+    // are fetched (clamped to the last array row) and never consumed: no branch in the step.
+#define ASYNC_STEP(J, EMIT)                                                                                 \
     {                                                                                                       \
         async_wait<ASYNC_NS - 2>();                                                                         \
         const double *slot = &S.ring[step & (ASYNC_NS - 1)][0][lane];                                       \
         const R rho(slot[0]), ua(slot[32]), ut(slot[64]), E(slot[96]);                                      \
-        {                                                                                                   \
-            const long long an = a + (ASYNC_NS - 1);                                                        \
-            if (an <= a_last)                                                                               \
-                async_issue_row(T, ring_lane, off_run, (int)((step + ASYNC_NS - 1) & (ASYNC_NS - 1)));      \
-            async_commit();                                                                                 \
-            if (off_run < off_max) off_run += A.pitch_in;   /* clamped at the last array row */             \
-        }                                                                                                   \
-        march_compute<R, DIV, RL, PROJ, EOS, true, J>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, emit, kc + J, m1, stage); \
+        async_issue_row(T, ring_lane, off_run, (int)((step + ASYNC_NS - 1) & (ASYNC_NS - 1)));              \
+        async_commit();                                                                                     \
+        off_run = off_run < off_max ? off_run + A.pitch_in : off_run;   /* clamped at the last array row */ \
+        march_compute<R, DIV, RL, PROJ, EOS, true, J, TR, EMIT>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, EMIT != 0, \
+                                                                kc + J, m1, stage);                         \
         a++; step++;                                                                                        \
     }
 
+    // warm-up: 8 steps fill the dependency cone of the first output, nothing is emitted
+    {
+        const int kc = 0;
 #pragma unroll 1
-    for (long long it = 0; it < n_iter; it++) {
-        const bool emit = it >= 2;
+        for (int it = 0; it < 2; it++) {
+            ASYNC_STEP(0, 0)
+            ASYNC_STEP(1, 0)
+            ASYNC_STEP(2, 0)
+            ASYNC_STEP(3, 0)
+        }
+    }
+    // steady state: every iteration emits 4 cells, every second one flushes the transposed staging tile
+#pragma unroll 1
+    for (long long it = 0; it < 2 * nchunks; it++) {
         const int kc = (int)(it & 1) * 4;
-        ASYNC_STEP(0)
-        ASYNC_STEP(1)
-        ASYNC_STEP(2)
-        ASYNC_STEP(3)
-        if (A.transpose_out && emit && (it & 1)) flush_stage(A, stage, w0, a - 12, m1);
+        ASYNC_STEP(0, 1)
+        ASYNC_STEP(1, 1)
+        ASYNC_STEP(2, 1)
+        ASYNC_STEP(3, 1)
+        if (TR == 1 && (it & 1)) flush_stage(A, stage, w0, a - 12, m1);
     }
 #undef ASYNC_STEP
     async_wait<0>();

@@ -84,21 +84,23 @@ sweep_fn_t sweep_tma_table_fast_biz(int rl, int proj);
         return table[rl][proj];                                                             \
     }
 
-// cp.async-staged marching kernels (sweep_async_kernel.cuh); same signature as the register-prefetch kernels.
-sweep_fn_t sweep_async_table_strict_pg(int rl, int proj);
-sweep_fn_t sweep_async_table_strict_biz(int rl, int proj);
-sweep_fn_t sweep_async_table_fast_pg(int rl, int proj);
-sweep_fn_t sweep_async_table_fast_biz(int rl, int proj);
+// cp.async-staged marching kernels (sweep_async_kernel.cuh); tr = 1: transposed output.
+sweep_fn_t sweep_async_table_strict_pg(int rl, int proj, int tr);
+sweep_fn_t sweep_async_table_strict_biz(int rl, int proj, int tr);
+sweep_fn_t sweep_async_table_fast_pg(int rl, int proj, int tr);
+sweep_fn_t sweep_async_table_fast_biz(int rl, int proj, int tr);
+
+#define ARMON_ASYNC_ROW(R, DIV, RLV, EOS)                                                    \
+    {{sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
+     {sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 0>, sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 1>}}
 
 #define ARMON_DEFINE_ASYNC_TABLE(NAME, R, DIV, EOS)                                          \
-    sweep_fn_t NAME(int rl, int proj)                                                       \
+    sweep_fn_t NAME(int rl, int proj, int tr)                                               \
     {                                                                                       \
-        static const sweep_fn_t table[4][2] = {                                             \
-            {sweep_async_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_async_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_async_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_async_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_async_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
+        static const sweep_fn_t table[4][2][2] = {                                          \
+            ARMON_ASYNC_ROW(R, DIV, 0, EOS), ARMON_ASYNC_ROW(R, DIV, 1, EOS),               \
+            ARMON_ASYNC_ROW(R, DIV, 2, EOS), ARMON_ASYNC_ROW(R, DIV, 3, EOS),               \
         };                                                                                  \
-        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
-        return table[rl][proj];                                                             \
+        if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
+        return table[rl][proj][tr];                                                         \
     }

@@ -126,8 +126,9 @@ __device__ __forceinline__ void issue_loads(const SweepArgs &A, const SweepThrea
 }
 
 // The arithmetic of one march step: consumes cell a (rho, ua, ut, E as read from memory), emits cell a-4 when `emit`.
-// J = (a - a_begin) & 3 is static.
-template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED, int J>
+// J = (a - a_begin) & 3 is static.  TR / EMIT: -1 = decided at run time (A.transpose_out / `emit`), 0 / 1 = known at
+// compile time, which makes the whole step one basic block for the instruction scheduler (no uniform branches).
+template <class R, int DIV, int RL, int PROJ, int EOS, bool STAGED, int J, int TR = -1, int EMIT = -1>
 __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T, Pipe<R> &P, R rho, R ua, R ut, R E,
                                               const long long a, const R dt,
                                               const typename Div<R, DIV>::Rcp &inv_dx, const bool emit,
@@ -225,13 +226,17 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
     }
 
     // ---- projection of cell k = a-4: src/projection_schemes.jl:23-41 ----
-    if (emit) {
+    if (EMIT == 1 || (EMIT == -1 && emit)) {
+        const bool transpose_out = TR == -1 ? (A.transpose_out != 0) : (TR == 1);
         const R dXr = P.dxl[S0] * P.Lr[S0];
         R t_r = dXr - (Anr - P.Ar);
         R t_ru = dXr * P.Lu[S0] - (Anru - P.Aru);
         R t_rt = dXr * P.Lt[S0] - (Anrt - P.Art);
         R t_rE = dXr * P.LE[S0] - (AnrE - P.ArE);
-        if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
+        if (DIV == DIV_FAST) {   // the refined reciprocal of a power of two is exact: no need to tell the cases apart
+            const R idx(inv_dx.r);
+            t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
+        } else if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
             const R idx(A.inv_dx);
             t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
         } else {
@@ -243,13 +248,15 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
         const long long m = a - 4;
         const bool store = T.valid && m < m1;
         // dtCFL accumulators (src/reductions.jl:14-20): max(|u+c|,|u-c|) == |u|+c, new velocities, c of this sweep's EOS
-        if (store) {
-            const unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
-            const unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+        {   // branch-free: cells that are not stored contribute 0
+            unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
+            unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+            ba = store ? ba : 0ULL;
+            bt = store ? bt : 0ULL;
             T.amax = ba > T.amax ? ba : T.amax;
             T.tmax = bt > T.tmax ? bt : T.tmax;
         }
-        if (STAGED && A.transpose_out) {
+        if (STAGED && transpose_out) {
             // stage[var][lane][k]: flushed as rows of SWEEP_CHUNK contiguous doubles by flush_stage()
             double *s = stage + (threadIdx.x & 31) * SWEEP_STAGE_PITCH + k_chunk;
             s[0 * 32 * SWEEP_STAGE_PITCH] = t_r.v;
@@ -257,7 +264,7 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
             s[2 * 32 * SWEEP_STAGE_PITCH] = o_ut.v;
             s[3 * 32 * SWEEP_STAGE_PITCH] = o_E.v;
         } else if (store) {
-            const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
+            const long long o = transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
             A.out[0][o] = t_r.v;
             A.out[1][o] = o_ua.v;
             A.out[2][o] = o_ut.v;

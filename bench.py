@@ -272,12 +272,42 @@ def run_gpu_arm(args):
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("bytes_per_launch") if traffic else None,
-                "peak_source": peak_src, "kernel": f"sweep_kernel<{args.math}, GAD+minmod, euler_2nd, perfect gas>",
+                "peak_source": peak_src, "kernel": f"sweep_{os.environ.get('ARMON_B200_KERNEL', 'async')}_kernel<{args.math}, GAD+minmod, euler_2nd, "
+                          f"{'bizarrium' if w['test'] == 'Bizarrium' else 'perfect gas'}>",
                 "avg_launch_ms": avg_sweep_s * 1e3, "launches_timed": int(sweep_n.value),
                 "algorithmic_bytes_per_launch": BYTES_PER_CELL_SWEEP * local_cells,
                 "sweep_share_of_step": sweep_ms.value / 1e3 / (ms.value / 1e3)}
 
     grid.close()
+
+    # ---- secondary figure: the bit-exact (strict) arithmetic mode, same workload, short run ----
+    strict = None
+    if args.math != "strict" and not args.no_strict:
+        sp = armon.ArmonParameters(test=w["test"], N=global_n, use_MPI=multi, P=P, rank=rank, proc_size=world,
+                                   maxcycle=10**9, math_mode="strict", march_segment=args.segment, bind_pcg=False,
+                                   device_id=local_rank, return_data=True, **scheme_kwargs())
+        sg = armon.BlockGrid(sp)
+        armon.init_test(sp, sg)
+        n_strict = min(args.steps, 10)
+        check(lib.armon_solver_run(sg.solver, 3))
+        dev2 = sg.device
+        dev2.wait()
+        if multi:
+            adist.barrier()
+        check(lib.armon_solver_profile(sg.solver, 1))
+        check(lib.armon_solver_run(sg.solver, n_strict))
+        sms = C.c_float()
+        check(lib.armon_solver_elapsed_ms(sg.solver, C.byref(sms)))
+        s_sweep_ms, s_sweep_n = C.c_double(), C.c_uint64()
+        check(lib.armon_solver_sweep_time_ms(sg.solver, C.byref(s_sweep_ms), C.byref(s_sweep_n)))
+        s_el = sms.value / 1e3
+        if multi:
+            s_el = adist.allreduce_max(s_el)
+        s_avg = s_sweep_ms.value / max(s_sweep_n.value, 1) / 1e3
+        strict = {"value": global_cells * n_strict / s_el / 1e9, "unit": UNIT, "steps": n_strict,
+                  "roofline_frac": BYTES_PER_CELL_SWEEP * local_cells / s_avg / 1e9 / peak,
+                  "avg_launch_ms": s_avg * 1e3, "note": "math_mode strict: bit-identical to the CPU oracle"}
+        sg.close()
     if rank != 0:
         return 0
 
@@ -301,6 +331,7 @@ def run_gpu_arm(args):
                    "timing": "CUDA events on the solver stream, max over ranks"},
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "strict_mode": strict,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "h2d of rho,u,v,E from pinned host memory + K x (solver_cycle + blocking read "
                 "of the time-step state) + finalize + d2h of rho,u,v,E, wall clock, max over ranks"},
@@ -316,14 +347,17 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sod_circ_8192", choices=sorted(WORKLOADS))
-    ap.add_argument("--math", default="strict", choices=["strict", "fast", "ieee"])
+    ap.add_argument("--math", default="fast", choices=["strict", "fast", "ieee"],
+                    help="fast: FMA + reciprocal division, the reference's own @fastmath latitude (default, within 1e-12 of "
+                         "the golden data); strict: bit-exact vs the oracle; ieee: strict with nvcc's full division")
     ap.add_argument("--segment", type=int, default=0, help="march segment length (0 = auto)")
     ap.add_argument("--proc-grid", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strict", action="store_true", help="skip the secondary strict-mode measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3   # timing rule: W >= 3
