@@ -421,7 +421,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
             ARMON_LAUNCH_CHECK(s->ctx);
         }
         s->sweep_index++;
-    } else if (s->use_async) {
+    } else if (s->use_async && (A.pitch_in % 2) == 0) {
         s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(AsyncWarpShared), s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
     } else if (s->use_tma && (A.pitch_in % 2) == 0) {
@@ -594,10 +594,24 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                     s->async_kernel[tr] = biz ? sweep_async_table_fast_biz(rl, desc->projection, tr)
                                               : sweep_async_table_fast_pg(rl, desc->projection, tr);
                 ok = ok && s->async_kernel[tr] != nullptr;
-                if (s->async_kernel[tr])
+                if (s->async_kernel[tr]) {
                     ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel[tr],
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared))));
+                    // the kernel stages everything through shared memory and has no use for L1: give the whole
+                    // unified array to shared memory so that ASYNC_MIN_BLOCKS CTAs are resident per SM
+                    const char *cv = getenv("ARMON_B200_CARVEOUT");   // percent of shared memory, -1 = driver default
+                    ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel[tr],
+                                                    cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                    cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+                    if (getenv("ARMON_B200_VERBOSE")) {
+                        int nb = 0;
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)s->async_kernel[tr], ASYNC_TPB,
+                                                                      ASYNC_TPB / 32 * sizeof(AsyncWarpShared));
+                        fprintf(stderr, "[armon_b200] async kernel tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n", tr, nb,
+                                (size_t)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared)));
+                    }
+                }
             }
             s->use_async = ok;
         }

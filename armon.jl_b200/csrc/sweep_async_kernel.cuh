@@ -5,11 +5,14 @@
 // register-prefetch kernel keeps the 4 rows in flight in 32 registers and the round-1 profile shows 15 % of its cycles
 // waiting on those loads (HBM latency under load exceeds a 4-row lead); the bulk-copy (TMA) variant of
 // sweep_tma_kernel.cuh removes the wait but pays ~45 issue slots per step for the elected-lane producer code.  Here
-// every thread copies its own 8 bytes of rho, ua, ut, E of the row ASYNC_NS - 1 steps ahead into a per-warp ring
-// [slot][variable][lane] with four `cp.async` instructions and one commit per step; the consumer side is one
-// `cp.async.wait_group` and four conflict-free 8-byte shared loads.  A thread only ever reads what it copied itself:
-// no barrier of any kind inside the march, no alignment requirement beyond 8 bytes (any pitch works), and the lead is
-// a compile-time constant that costs shared memory instead of registers.
+// the warp copies the 4 x 256 bytes (rho, ua, ut, E of its 32 columns) of the row ASYNC_NS - 1 steps ahead into a
+// per-warp ring [slot][variable][lane] with two 16-byte `cp.async.cg` per thread (lanes 0-15: variables 0 and 2, lanes
+// 16-31: variables 1 and 3) and one commit per step; the consumer side is one `cp.async.wait_group`, a warp barrier and
+// four conflict-free 8-byte shared loads.  `.cg` bypasses L1: with the 8-byte `.ca` form every row in flight pins L1
+// lines (57 KB per SM at 7 rows x 8 warps), and the measured time followed the L1 size left over by the shared-memory
+// carve-out (1.05 ms at the default carve-out, 1.23 ms with all of the array given to shared memory).  The lead is a
+// compile-time constant that costs shared memory instead of registers.  16-byte copies need an even pitch and
+// 16-byte aligned arrays; the host falls back to sweep_kernel otherwise.
 #pragma once
 
 #include "sweep_kernel.cuh"
@@ -24,19 +27,27 @@ struct AsyncWarpShared {
     double stage[4 * 32 * SWEEP_STAGE_PITCH];              // transposed-store staging (flush_stage)
 };
 
-__device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
+__device__ __forceinline__ void async_copy16(unsigned dst, const double *src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// copies of the thread's cell of the array row whose first cell has element offset `off` into ring slot `s`
-__device__ __forceinline__ void async_issue_row(const SweepThread &T, unsigned ring_lane, long long off, int s)
+// Per-thread copy plan: 16 bytes (2 columns) of two variables per array row.
+struct AsyncLane {
+    const double *src[2];   // A.in[2j + (lane >> 4)] + w0 + g + 2 * (lane & 15)
+    unsigned dst[2];        // shared address of ring[0][2j + (lane >> 4)][2 * (lane & 15)]
+    bool active;            // the two columns exist (ragged last warp of a row)
+};
+
+// copies of the array row whose first cell has element offset `off` into ring slot `s`
+__device__ __forceinline__ void async_issue_row(const AsyncLane &L, long long off, int s)
 {
-    const unsigned dst = ring_lane + 1024u * (unsigned)s;
-#pragma unroll
-    for (int k = 0; k < 4; k++) async_copy8(dst + 256u * k, T.base[k] + off);
+    if (L.active) {
+        async_copy16(L.dst[0] + 1024u * (unsigned)s, L.src[0] + off);
+        async_copy16(L.dst[1] + 1024u * (unsigned)s, L.src[1] + off);
+    }
 }
 
 #ifndef ASYNC_MIN_BLOCKS
@@ -81,15 +92,27 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
     const R dt = R(ts->current_dt) * R(A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
     const long long nchunks = (m1 - m0 + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
     const long long a_begin = m0 - 4;
-    const long long a_last = m0 + nchunks * SWEEP_CHUNK + 3;   // last cell index consumed
 
     // prologue: rows a_begin .. a_begin + ASYNC_NS - 2, one commit group per row (a segment has >= 16 steps);
     // afterwards step t fetches row a_begin + t + ASYNC_NS - 1 into the slot consumed at step t - 1
     static_assert(ASYNC_NS >= 2 && ASYNC_NS <= 16 && (ASYNC_NS & (ASYNC_NS - 1)) == 0, "ring size");
-    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(&S.ring[0][0][lane]);
+    AsyncLane L;
+    {
+        const int h = lane >> 4, piece = lane & 15;
+        const long long cols = A.nw - w0 < 32 ? A.nw - w0 : 32;
+        L.active = 2 * piece < cols;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            L.src[j] = (h ? A.in[2 * j + 1] : A.in[2 * j]) + w0 + A.g + 2 * piece;
+            L.dst[j] = (unsigned)__cvta_generic_to_shared(&S.ring[0][2 * j + h][2 * piece]);
+        }
+        // columns past the end of the row are never copied: give those lanes a benign finite state (rho = E = 1, u = v = 0)
+        for (int k = lane; k < ASYNC_NS * 4 * 32; k += 32) (&S.ring[0][0][0])[k] = ((k >> 5) & 3) == 0 || ((k >> 5) & 3) == 3 ? 1.0 : 0.0;
+        __syncwarp();
+    }
 #pragma unroll 1
     for (int s = 0; s < ASYNC_NS - 1; s++) {
-        async_issue_row(T, ring_lane, march_row_offset(A, a_begin + s), s);
+        async_issue_row(L, march_row_offset(A, a_begin + s), s);
         async_commit();
     }
     long long off_run = march_row_offset(A, a_begin + ASYNC_NS - 1);   // offset of row a + ASYNC_NS - 1
@@ -117,9 +140,10 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
 #define ASYNC_STEP(J, EMIT)                                                                                 \
     {                                                                                                       \
         async_wait<ASYNC_NS - 2>();                                                                         \
+        __syncwarp();   /* every lane's copies of this row have landed; the slot refilled below was read a step ago */ \
         const double *slot = &S.ring[step & (ASYNC_NS - 1)][0][lane];                                       \
         const R rho(slot[0]), ua(slot[32]), ut(slot[64]), E(slot[96]);                                      \
-        async_issue_row(T, ring_lane, off_run, (int)((step + ASYNC_NS - 1) & (ASYNC_NS - 1)));              \
+        async_issue_row(L, off_run, (int)((step + ASYNC_NS - 1) & (ASYNC_NS - 1)));                         \
         async_commit();                                                                                     \
         off_run = off_run < off_max ? off_run + A.pitch_in : off_run;   /* clamped at the last array row */ \
         march_compute<R, DIV, RL, PROJ, EOS, true, J, TR, EMIT>(A, T, P, rho, ua, ut, E, a, dt, inv_dx, EMIT != 0, \
