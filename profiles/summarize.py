@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Reduce an ncu report (.ncu-rep, `--set full`) to the metrics quoted in DESIGN.md / profiles/README.md.
+
+  python profiles/summarize.py gpurun_out/prof.ncu-rep profiles/out_summary.csv [--traffic profiles/sweep_traffic.json]
+"""
+import csv
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.per_cycle_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+    "smsp__inst_executed.sum", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    stall = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+    cols = [k for k in KEYS if k in hdr] + stall
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(cols)
+        w.writerow([units[hdr.index(c)] for c in cols])
+        for r in rows[2:]:
+            w.writerow([r[hdr.index(c)] for c in cols])
+    if "--traffic" in sys.argv:
+        d = dict(zip(hdr, rows[2]))
+        u = dict(zip(hdr, units))
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        rd = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]]
+        wr = float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
+        with open(sys.argv[sys.argv.index("--traffic") + 1], "w") as f:
+            json.dump({"kernel": d["Kernel Name"], "grid": d["Grid Size"], "dram_bytes_read": rd, "dram_bytes_write": wr,
+                       "bytes_per_launch": rd + wr, "source": rep.split("/")[-1],
+                       "note": "ncu --set full --clock-control none, one launch of the sweep kernel at 8192x8192"}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
