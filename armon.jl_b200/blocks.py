@@ -79,7 +79,7 @@ def solver_desc(params):
         d.neighbours[int(s)] = params.neighbours[s]
     d.math_mode = backend.MATH_MODES[params.math_mode]
     d.march_segment = params.march_segment
-    d.kernel_variant = {"auto": 0, "single": 1, "ws": 2, "tma": 3, "async": 4}[params.kernel_variant]
+    d.kernel_variant = {"auto": 0, "single": 1, "ws": 2, "tma": 3, "async": 4, "async2": 5}[params.kernel_variant]
     fill_test_case(d.tc, params.test)
     return d
 

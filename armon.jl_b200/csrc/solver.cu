@@ -247,6 +247,7 @@ struct armon_solver {
     // cp.async-staged marching kernel (sweep_async_kernel.cuh)
     sweep_fn_t        async_kernel[2] = {nullptr, nullptr};   // [transposed output]
     bool              use_async = false;
+    size_t            async_smem = 0;      // dynamic shared memory per CTA of the selected async kernel
     unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
     uint64_t          sweep_index = 0;
@@ -422,7 +423,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         }
         s->sweep_index++;
     } else if (s->use_async && (A.pitch_in % 2) == 0) {
-        s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(AsyncWarpShared), s->ctx->stream>>>(A);
+        s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->async_smem, s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
     } else if (s->use_tma && (A.pitch_in % 2) == 0) {
         s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), s->ctx->stream>>>(A);
@@ -568,8 +569,9 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     {
         const char *env = getenv("ARMON_B200_KERNEL");
         // measured at 8192^2 (profiles/): strict 3.25 ms (ws) vs 3.48 ms (single); fast 2.23 ms (ws) vs 1.88 ms (single)
-        // kernel_variant / ARMON_B200_KERNEL: 0 auto (= cp.async-staged), 1 single (register prefetch), 2 ws, 3 tma, 4 async.
-        // Measured at 8192^2, fast mode (profiles/): async 1.18 ms, tma 1.55 ms, single 1.68 ms, ws 2.2 ms per sweep.
+        // kernel_variant / ARMON_B200_KERNEL: 0 auto (= async2), 1 single (register prefetch), 2 ws, 3 tma, 4 async,
+        // 5 async2 (cp.async staging + software-pipelined step).  Measured at 8192^2, fast mode (profiles/README.md):
+        // async2 0.99 ms, async 1.03 ms, tma 1.55 ms, single 1.68 ms, ws 2.2 ms per sweep.
         const bool want_tma = env ? (std::string(env) == "tma") : (desc->kernel_variant == 3);
         if (want_tma && desc->math_mode != ARMON_MATH_IEEE) {
             if (desc->math_mode == ARMON_MATH_STRICT)
@@ -582,12 +584,22 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                 s->use_tma = true;
             }
         }
-        const bool want_async = !s->use_tma && (env ? (std::string(env) == "async" || std::string(env) == "auto")
-                                                    : (desc->kernel_variant == 4 || desc->kernel_variant == 0));
+        const bool want_async2 = !s->use_tma && (env ? (std::string(env) == "async2" || std::string(env) == "auto")
+                                                     : (desc->kernel_variant == 5 || desc->kernel_variant == 0));
+        const bool want_async = !s->use_tma && (want_async2 || (env ? (std::string(env) == "async")
+                                                                   : (desc->kernel_variant == 4)));
         if (want_async && desc->math_mode != ARMON_MATH_IEEE) {
             bool ok = true;
+            s->async_smem = ASYNC_TPB / 32 * (want_async2 ? sizeof(Async2WarpShared) : sizeof(AsyncWarpShared));
             for (int tr = 0; tr < 2; tr++) {
-                if (desc->math_mode == ARMON_MATH_STRICT)
+                if (want_async2) {
+                    if (desc->math_mode == ARMON_MATH_STRICT)
+                        s->async_kernel[tr] = biz ? sweep_async2_table_strict_biz(rl, desc->projection, tr)
+                                                  : sweep_async2_table_strict_pg(rl, desc->projection, tr);
+                    else
+                        s->async_kernel[tr] = biz ? sweep_async2_table_fast_biz(rl, desc->projection, tr)
+                                                  : sweep_async2_table_fast_pg(rl, desc->projection, tr);
+                } else if (desc->math_mode == ARMON_MATH_STRICT)
                     s->async_kernel[tr] = biz ? sweep_async_table_strict_biz(rl, desc->projection, tr)
                                               : sweep_async_table_strict_pg(rl, desc->projection, tr);
                 else
@@ -596,8 +608,7 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                 ok = ok && s->async_kernel[tr] != nullptr;
                 if (s->async_kernel[tr]) {
                     ARMON_CUDA(cudaFuncSetAttribute((const void *)s->async_kernel[tr],
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared))));
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->async_smem));
                     // the kernel stages everything through shared memory and has no use for L1: give the whole
                     // unified array to shared memory so that ASYNC_MIN_BLOCKS CTAs are resident per SM
                     const char *cv = getenv("ARMON_B200_CARVEOUT");   // percent of shared memory, -1 = driver default
@@ -607,9 +618,9 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                     if (getenv("ARMON_B200_VERBOSE")) {
                         int nb = 0;
                         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)s->async_kernel[tr], ASYNC_TPB,
-                                                                      ASYNC_TPB / 32 * sizeof(AsyncWarpShared));
-                        fprintf(stderr, "[armon_b200] async kernel tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n", tr, nb,
-                                (size_t)(ASYNC_TPB / 32 * sizeof(AsyncWarpShared)));
+                                                                      s->async_smem);
+                        fprintf(stderr, "[armon_b200] async%s kernel tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n",
+                                want_async2 ? "2" : "", tr, nb, s->async_smem);
                     }
                 }
             }

@@ -236,7 +236,7 @@ class ArmonParameters:
         self.march_segment = int(march_segment)
         self.fused = bool(fused)
         self.bind_pcg = bool(bind_pcg)
-        if kernel_variant not in ("auto", "single", "ws", "tma", "async"):
+        if kernel_variant not in ("auto", "single", "ws", "tma", "async", "async2"):
             solver_error("config", f"unknown kernel_variant '{kernel_variant}'")
         self.kernel_variant = kernel_variant   # "ws": warp-specialised producer/consumer kernel; "tma": TMA-staged inputs
         self.device_id = int(os.environ.get("LOCAL_RANK", 0)) if device_id is None else int(device_id)

@@ -100,7 +100,7 @@ typedef struct {
     int32_t neighbours[4];           /* rank of the neighbour per side, -1 = global edge (MPI.PROC_NULL), params.neighbours */
     int32_t math_mode;               /* ARMON_MATH_* */
     int32_t march_segment;           /* cells per marching segment along the swept axis (0 = auto) */
-    int32_t kernel_variant;          /* 0 = auto, 1 = register-prefetch marching kernel, 2 = warp-specialised (producer/consumer), 3 = TMA-staged inputs, 4 = cp.async-staged inputs */
+    int32_t kernel_variant;          /* 0 = auto, 1 = register-prefetch marching kernel, 2 = warp-specialised (producer/consumer), 3 = TMA-staged inputs, 4 = cp.async-staged inputs, 5 = cp.async-staged, software-pipelined step */
     armon_test_case tc;
 } armon_solver_desc;
 

@@ -92,7 +92,7 @@ def test_golden_vectors(test, fused, golden):
 
 
 # ---- 3. fused strict path == oracle, bit for bit --------------------------------------------------------
-@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async"])
+@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async", "async2"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
 def test_fused_strict_bit_exact_on_golden_cases(test, variant):
     stats, grid = run_gpu(reference_params(test, kernel_variant=variant))
@@ -118,7 +118,7 @@ VARIANTS = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async"])
+@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async", "async2"])
 @pytest.mark.parametrize("test,N,scheme,limiter,projection,splitting,cycles", VARIANTS)
 def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, splitting, cycles, variant):
     kw = dict(N=N, scheme=scheme, riemann_limiter=limiter, projection=projection, axis_splitting=splitting,
@@ -133,7 +133,7 @@ def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, s
     grid.close()
 
 
-@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async"])
+@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async", "async2"])
 @pytest.mark.parametrize("seg", [8, 16, 40, 1000])
 def test_march_segment_does_not_change_results(seg, variant):
     kw = dict(N=(90, 75), maxcycle=8)
@@ -156,7 +156,7 @@ def test_cst_dt():
 
 
 # ---- 4. fast arithmetic mode: 1e-12 of field scale -------------------------------------------------------
-@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async"])
+@pytest.mark.parametrize("variant", ["single", "ws", "tma", "async", "async2"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
 def test_fused_fast_mode_within_tolerance(test, variant, golden):
     ref = golden(test)
