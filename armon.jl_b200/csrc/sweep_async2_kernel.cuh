@@ -8,10 +8,12 @@
 // head of the chain runs one step ahead of the rest:
 //
 //   stage A (cell a)        : EOS(a), Godunov interface a                       -- uses nothing produced in this step
-//   stages B-E (one behind) : GAD flux a-2, Lagrangian cell a-3, slopes of cell a-4, advection flux a-4,
-//                             projection of cell a-5                            -- use Godunov states up to a-1 only
+//   stage B (one behind)    : GAD flux at interface a-2                         -- uses Godunov states up to a-1 only
+//   stages C-E (two behind) : Lagrangian cell a-4, slopes of cell a-5, advection flux a-5, projection of cell a-6
+//                                                                               -- use fluxes up to a-3 only
 //
-// so that the scheduler always has an independent 45-instruction chain to interleave with the other ~260.
+// so that the scheduler always has three independent chains to interleave (A2_SKEW = 0 keeps B-E together, one step
+// behind A).  Results of A and B are committed to the register rings at the end of the step.
 // Registers: the skew costs one more live slot of (ua, p, rho*c, rho*dx, Godunov state); to pay for it the values that
 // merely ride along the pipeline are left in shared memory instead: ut and E of a cell are re-read from the input ring
 // when the Lagrangian update (3 steps later) and the projection (5 steps later) need them, and the sound speed goes
@@ -20,9 +22,13 @@
 
 #include "sweep_async_kernel.cuh"
 
-constexpr int A2_NS = 16;        // input ring slots per warp
-constexpr int A2_KEEP = 6;       // consumed rows that must stay readable (rows a .. a-5)
-constexpr int A2_CS = 8;         // sound-speed ring slots (written at a, read at a-5)
+#ifndef A2_SKEW
+#define A2_SKEW 0                // 0: only EOS+Godunov run ahead (measured best: 0.99 ms); 1: the GAD flux also runs ahead of the Lagrangian update (252 registers, 1.01 ms)
+#endif
+constexpr int A2_Q = A2_SKEW;
+constexpr int A2_NS = 16;            // input ring slots per warp
+constexpr int A2_KEEP = 6 + A2_Q;    // consumed rows that must stay readable (rows a .. a-5-q)
+constexpr int A2_CS = 8;             // sound-speed ring slots (written at a, read at a-5-q)
 
 struct Async2WarpShared {
     double ring[A2_NS][4][32];                             // [slot][variable][lane]
@@ -50,29 +56,36 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
                                                const long long m1, double *stage)
 {
     typedef Div<R, DIV> D;
-    constexpr int Z0 = J & 3, Z1 = (J + 3) & 3, Z2 = (J + 2) & 3, Z3 = (J + 1) & 3;   // slots of cells a, a-1, a-2, a-3
-    constexpr int Z4 = Z0, Z5 = Z1;                                                   // cells a-4, a-5
+    // slot of cell / interface a-k in the 4-entry rings
+#define ZS(k) ((J + 8 - (k)) & 3)
+    constexpr int q = A2_Q;
+    constexpr int Z0 = ZS(0), Z1 = ZS(1), Z2 = ZS(2), Z3 = ZS(3);
+    constexpr int ZL = ZS(3 + q), ZLn = ZS(2 + q);   // Lagrangian cell a-3-q: its own slot, slot of its right interface
+    constexpr int ZM = ZS(5 + q), ZC = ZS(4 + q), ZP = ZS(3 + q);   // slope / advection: cells a-5-q, a-4-q, a-3-q
     const R dx(A.dx);
     RangeFlag &f = T.flag;
     const double *row0 = ring + ((step) & (A2_NS - 1)) * 128;
-    const double *row3 = ring + ((step - 3) & (A2_NS - 1)) * 128;
-    const double *row5 = ring + ((step - 5) & (A2_NS - 1)) * 128;
+    const double *rowL = ring + ((step - 3 - q) & (A2_NS - 1)) * 128;
+    const double *rowE = ring + ((step - 5 - q) & (A2_NS - 1)) * 128;
 
     // ---- stage A, cell a: EOS (src/kernels.jl:4-55), Godunov state at interface a (src/riemann_schemes.jl:21-30) ----
+    // results are committed to the rings at the end of the step: with q = 1 the slots still hold cell a-4
+    R A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp;
     {
         const R rho(row0[0]), ua(row0[32]), ut(row0[64]), E(row0[96]);
         R p, c;
         eos_eval<R, DIV, EOS>(A, rho, ua, ut, E, p, c, f);
         const R rc = rho * c;
         cring[(step & (A2_CS - 1)) * 32] = c.v;
-        acoustic_godunov<R, DIV>(P.crc[Z1], rc, P.cu[Z1], ua, P.cp[Z1], p, P.Gu[Z0], P.Gp[Z0], f);
-        P.cu[Z0] = ua; P.cp[Z0] = p; P.crc[Z0] = rc; P.cdm[Z0] = rho * dx;
+        acoustic_godunov<R, DIV>(P.crc[Z1], rc, P.cu[Z1], ua, P.cp[Z1], p, A_Gu, A_Gp, f);
+        A_ua = ua; A_p = p; A_rc = rc; A_dm = rho * dx;
     }
 
     // ---- stage B, flux at interface i = a-2 (cells a-3, a-2); Godunov states a-3, a-2, a-1 come from earlier steps ----
+    R B_Fu, B_Fp;
     if (RL == 0) {   // acoustic!  src/riemann_schemes.jl:33-43
-        P.Fu[Z2] = P.Gu[Z2];
-        P.Fp[Z2] = P.Gp[Z2];
+        B_Fu = P.Gu[Z2];
+        B_Fp = P.Gp[Z2];
     } else {         // acoustic_GAD!  src/riemann_schemes.jl:55-104
         constexpr int LIM = RL - 1;
         const R u_i = P.cu[Z2], u_im = P.cu[Z3], p_i = P.cp[Z2], p_im = P.cp[Z3];
@@ -86,70 +99,73 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         }
         const R Dm = (P.cdm[Z3] + P.cdm[Z2]) * R(0.5);                                   // (dm_l + dm_r) / 2
         const R theta = R(0.5) * (R(1.) - ((P.crc[Z3] + P.crc[Z2]) * R(0.5)) * D::div(dt, Dm, f));
-        P.Fu[Z2] = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
-        P.Fp[Z2] = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
+        B_Fu = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
+        B_Fp = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
     }
-    P.FpFu[Z2] = P.Fp[Z2] * P.Fu[Z2];
-    P.disp[Z2] = dt * P.Fu[Z2];
+    const R B_FpFu = B_Fp * B_Fu;
+    const R B_disp = dt * B_Fu;
+    if (q == 0) {   // the Lagrangian update below uses this flux right away
+        P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu; P.disp[Z2] = B_disp;
+    }
 
-    // ---- stage C, Lagrangian update of cell k = a-3: src/kernels.jl:58-68 (ut, E of the cell re-read from the ring) ----
+    // ---- stage C, Lagrangian update of cell k = a-3-q: src/kernels.jl:58-68 (ut, E of the cell re-read from the ring) ----
     {
-        const R dxl = dx + dt * (P.Fu[Z2] - P.Fu[Z3]);
-        const R dm = P.cdm[Z3];
+        const R dxl = dx + dt * (P.Fu[ZLn] - P.Fu[ZL]);
+        const R dm = P.cdm[ZL];
         const R dtdm = D::div(dt, dm, f);
         const R Lr = D::div(dm, dxl, f);
-        const R Lu = P.cu[Z3] + dtdm * (P.Fp[Z3] - P.Fp[Z2]);
-        const R LE = R(row3[96]) + dtdm * (P.FpFu[Z3] - P.FpFu[Z2]);
-        const R Lt(row3[64]);
-        P.dxl[Z3] = dxl; P.Lr[Z3] = Lr; P.Lu[Z3] = Lu; P.LE[Z3] = LE;
-        P.Lru[Z3] = Lr * Lu; P.Lrt[Z3] = Lr * Lt; P.LrE[Z3] = Lr * LE;
+        const R Lu = P.cu[ZL] + dtdm * (P.Fp[ZL] - P.Fp[ZLn]);
+        const R LE = R(rowL[96]) + dtdm * (P.FpFu[ZL] - P.FpFu[ZLn]);
+        const R Lt(rowL[64]);
+        P.dxl[ZL] = dxl; P.Lr[ZL] = Lr; P.Lu[ZL] = Lu; P.LE[ZL] = LE;
+        P.Lru[ZL] = Lr * Lu; P.Lrt[ZL] = Lr * Lt; P.LrE[ZL] = Lr * LE;
     }
 
-    // ---- stage D, advection flux at interface is = a-4: src/projection_schemes.jl:62-124 (see march_compute) ----
-    // cells a-5 -> Z5, a-4 -> Z4, a-3 -> Z3 ; disp(a-5) -> Z5, disp(a-4) -> Z4, disp(a-3) -> Z3
+    // ---- stage D, advection flux at interface is = a-4-q: src/projection_schemes.jl:62-124 (see march_compute) ----
+    // cells a-5-q -> ZM, a-4-q -> ZC, a-3-q -> ZP ; disp of the same interfaces in the same slots
     R Anr, Anru, Anrt, AnrE;
     {
-        const R d = P.disp[Z4];
+        const R d = P.disp[ZC];
         const bool pos = d.v > 0.0;
         if (PROJ == ARMON_PROJ_EULER_2ND) {
-            const R dxl_m = P.dxl[Z5], dxl_0 = P.dxl[Z4], dxl_p = P.dxl[Z3];
+            const R dxl_m = P.dxl[ZM], dxl_0 = P.dxl[ZC], dxl_p = P.dxl[ZP];
             const R two_dxl = R(2.) * dxl_0;
             const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
             const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
             const typename D::Rcp k2 = D::prepare(two_dxl, f);
-            const R sr = slope_minmod_fused<R>(P.Lr[Z5], P.Lr[Z4], P.Lr[Z3], r_m, r_p);
-            const R sru = slope_minmod_fused<R>(P.Lru[Z5], P.Lru[Z4], P.Lru[Z3], r_m, r_p);
-            const R srt = slope_minmod_fused<R>(P.Lrt[Z5], P.Lrt[Z4], P.Lrt[Z3], r_m, r_p);
-            const R srE = slope_minmod_fused<R>(P.LrE[Z5], P.LrE[Z4], P.LrE[Z3], r_m, r_p);
+            const R sr = slope_minmod_fused<R>(P.Lr[ZM], P.Lr[ZC], P.Lr[ZP], r_m, r_p);
+            const R sru = slope_minmod_fused<R>(P.Lru[ZM], P.Lru[ZC], P.Lru[ZP], r_m, r_p);
+            const R srt = slope_minmod_fused<R>(P.Lrt[ZM], P.Lrt[ZC], P.Lrt[ZP], r_m, r_p);
+            const R srE = slope_minmod_fused<R>(P.LrE[ZM], P.LrE[ZC], P.LrE[ZP], r_m, r_p);
 
-            const R dxe = rsel(pos, -(dx - P.disp[Z5]), dx + P.disp[Z3]);
+            const R dxe = rsel(pos, -(dx - P.disp[ZM]), dx + P.disp[ZP]);
             typename D::Rcp ksel;
             ksel.b = pos ? P.S2b.v : k2.b;
             ksel.r = pos ? P.S2r.v : k2.r;
             const R lf = D::quot(dxe, ksel, f);
-            Anr = d * (rsel(pos, P.Lr[Z5], P.Lr[Z4]) - rsel(pos, P.Sr, sr) * lf);
-            Anru = d * (rsel(pos, P.Lru[Z5], P.Lru[Z4]) - rsel(pos, P.Sru, sru) * lf);
-            Anrt = d * (rsel(pos, P.Lrt[Z5], P.Lrt[Z4]) - rsel(pos, P.Srt, srt) * lf);
-            AnrE = d * (rsel(pos, P.LrE[Z5], P.LrE[Z4]) - rsel(pos, P.SrE, srE) * lf);
+            Anr = d * (rsel(pos, P.Lr[ZM], P.Lr[ZC]) - rsel(pos, P.Sr, sr) * lf);
+            Anru = d * (rsel(pos, P.Lru[ZM], P.Lru[ZC]) - rsel(pos, P.Sru, sru) * lf);
+            Anrt = d * (rsel(pos, P.Lrt[ZM], P.Lrt[ZC]) - rsel(pos, P.Srt, srt) * lf);
+            AnrE = d * (rsel(pos, P.LrE[ZM], P.LrE[ZC]) - rsel(pos, P.SrE, srE) * lf);
             P.Sr = sr; P.Sru = sru; P.Srt = srt; P.SrE = srE;
             P.S2b = R(k2.b); P.S2r = R(k2.r);
         } else {
-            Anr = d * rsel(pos, P.Lr[Z5], P.Lr[Z4]);
-            Anru = d * rsel(pos, P.Lru[Z5], P.Lru[Z4]);
-            Anrt = d * rsel(pos, P.Lrt[Z5], P.Lrt[Z4]);
-            AnrE = d * rsel(pos, P.LrE[Z5], P.LrE[Z4]);
+            Anr = d * rsel(pos, P.Lr[ZM], P.Lr[ZC]);
+            Anru = d * rsel(pos, P.Lru[ZM], P.Lru[ZC]);
+            Anrt = d * rsel(pos, P.Lrt[ZM], P.Lrt[ZC]);
+            AnrE = d * rsel(pos, P.LrE[ZM], P.LrE[ZC]);
         }
     }
 
-    // ---- stage E, projection of cell k = a-5: src/projection_schemes.jl:23-41 ----
+    // ---- stage E, projection of cell k = a-5-q: src/projection_schemes.jl:23-41 ----
     if (EMIT == 1) {
-        const R dXr = P.dxl[Z5] * P.Lr[Z5];
-        const R Lt(row5[64]);
-        const R c_out(cring[((step - 5) & (A2_CS - 1)) * 32]);
+        const R dXr = P.dxl[ZM] * P.Lr[ZM];
+        const R Lt(rowE[64]);
+        const R c_out(cring[((step - 5 - q) & (A2_CS - 1)) * 32]);
         R t_r = dXr - (Anr - P.Ar);
-        R t_ru = dXr * P.Lu[Z5] - (Anru - P.Aru);
+        R t_ru = dXr * P.Lu[ZM] - (Anru - P.Aru);
         R t_rt = dXr * Lt - (Anrt - P.Art);
-        R t_rE = dXr * P.LE[Z5] - (AnrE - P.ArE);
+        R t_rE = dXr * P.LE[ZM] - (AnrE - P.ArE);
         if (DIV == DIV_FAST) {   // the refined reciprocal of a power of two is exact: no need to tell the cases apart
             const R idx(inv_dx.r);
             t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
@@ -162,7 +178,7 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         }
         const typename D::Rcp inv_r = D::prepare(t_r, f);
         const R o_ua = D::quot(t_ru, inv_r, f), o_ut = D::quot(t_rt, inv_r, f), o_E = D::quot(t_rE, inv_r, f);
-        const long long m = a - 5;
+        const long long m = a - 5 - q;
         const bool store = T.valid && m < m1;
         {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored contribute 0
             unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
@@ -187,6 +203,13 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         }
     }
     P.Ar = Anr; P.Aru = Anru; P.Art = Anrt; P.ArE = AnrE;
+
+    // ---- commit the results of the stages that ran ahead (their ring slots were still being read above) ----
+    P.cu[Z0] = A_ua; P.cp[Z0] = A_p; P.crc[Z0] = A_rc; P.cdm[Z0] = A_dm; P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
+    if (q == 1) {
+        P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu; P.disp[Z2] = B_disp;
+    }
+#undef ZS
 }
 
 #ifndef ASYNC2_MIN_BLOCKS
@@ -246,10 +269,10 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         for (int k = lane; k < A2_CS * 32; k += 32) (&S.cring[0][0])[k] = 1.0;
         __syncwarp();
     }
-    // Ring protocol: step t consumes row a_begin + t from slot t mod 16 and keeps rows t .. t-5 readable; it refills
-    // the slot of row t-6 with row t + 10.  Prologue: rows 0 .. 9, one commit group per row; one group per step
-    // afterwards, so the group of row t is complete once at most A2_NS - A2_KEEP - 1 = 9 groups are pending.
-    constexpr int LEAD = A2_NS - A2_KEEP;   // 10
+    // Ring protocol: step t consumes row a_begin + t from slot t mod 16 and keeps rows t .. t-KEEP+1 readable; it
+    // refills the slot of row t-KEEP with row t + LEAD.  Prologue: rows 0 .. LEAD-1, one commit group per row; one group
+    // per step afterwards, so the group of row t is complete once at most LEAD - 1 groups are pending.
+    constexpr int LEAD = A2_NS - A2_KEEP;   // 10 - q
 #pragma unroll 1
     for (int s = 0; s < LEAD; s++) {
         async_issue_row(L, march_row_offset(A, a_begin + s), s);
@@ -287,7 +310,7 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         a++; step++;                                                                                        \
     }
 
-    // warm-up: 9 steps fill the dependency cone of the first output (emitted at a = m0 + 5), nothing is emitted
+    // warm-up: 9 + q steps fill the dependency cone of the first output (emitted at a = m0 + 5 + q), nothing is emitted
 #pragma unroll 1
     for (int it = 0; it < 2; it++) {
         A2_STEP(0, 0, 0)
@@ -296,15 +319,16 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         A2_STEP(3, 0, 0)
     }
     A2_STEP(0, 0, 0)
+    if (A2_Q == 1) A2_STEP(1, 0, 0)
     // steady state: every iteration emits 4 cells, every second one flushes the transposed staging tile
 #pragma unroll 1
     for (long long it = 0; it < 2 * nchunks; it++) {
         const int kc = (int)(it & 1) * 4;
-        A2_STEP(1, 1, kc + 0)
-        A2_STEP(2, 1, kc + 1)
-        A2_STEP(3, 1, kc + 2)
-        A2_STEP(0, 1, kc + 3)
-        if (TR == 1 && (it & 1)) flush_stage(A, stage, w0, a - 13, m1);
+        A2_STEP((1 + A2_Q) & 3, 1, kc + 0)
+        A2_STEP((2 + A2_Q) & 3, 1, kc + 1)
+        A2_STEP((3 + A2_Q) & 3, 1, kc + 2)
+        A2_STEP((4 + A2_Q) & 3, 1, kc + 3)
+        if (TR == 1 && (it & 1)) flush_stage(A, stage, w0, a - 13 - A2_Q, m1);
     }
 #undef A2_STEP
     async_wait<0>();
