@@ -92,21 +92,26 @@ __global__ void k_cycle_step(DeviceTimeState *ts, CycleStepArgs a)
 
 // EOS_init + the first local_time_step (src/solver.jl:291-297): CFL maxima of the initial state.
 // Works on either layout: the reduction does not care about cell order.
+constexpr int INIT_DT_ROWS = 32;
 template <int EOS>
 __global__ void k_init_dt(long long n_rows, long long n_cols, long long pitch, int g, const double *rho,
                           const double *u, const double *v, const double *E, double gamma, DeviceTimeState *ts)
 {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long r = blockIdx.y;
     unsigned long long bx = 0ULL, by = 0ULL;
-    if (col < n_cols && r < n_rows) {
+    // INIT_DT_ROWS rows per block: one pair of atomics per warp and 32 rows instead of per row (the maxima are
+    // order-independent, so the grouping does not change the result)
+    for (long long r = (long long)blockIdx.y * INIT_DT_ROWS; r < n_rows && r < ((long long)blockIdx.y + 1) * INIT_DT_ROWS; r++) {
+        if (col >= n_cols) break;
         const long long i = (r + g) * pitch + (col + g);
         sd p, c, gg;
         RangeFlag f;
         if (EOS == ARMON_EOS_BIZARRIUM) eos_bizarrium<sd, DIV_IEEE, false>(sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, gg, f);
         else eos_perfect_gas<sd, DIV_IEEE>(sd(gamma), sd(rho[i]), sd(u[i]), sd(v[i]), sd(E[i]), p, c, f);
-        bx = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(u[i]), c.v));
-        by = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(v[i]), c.v));
+        const unsigned long long cx = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(u[i]), c.v));
+        const unsigned long long cy = (unsigned long long)__double_as_longlong(__dadd_rn(fabs(v[i]), c.v));
+        bx = cx > bx ? cx : bx;
+        by = cy > by ? cy : by;
     }
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long ox = __shfl_xor_sync(0xffffffffu, bx, off);
@@ -476,7 +481,7 @@ int launch_init_dt(armon_solver *s)
     const long long n_rows = s->cur_transposed ? D.nx : D.ny, n_cols = s->cur_transposed ? D.ny : D.nx;
     const long long pitch = n_cols + 2 * D.g;
     double *const *b = s->buf[s->cur];
-    const dim3 grid((unsigned)((n_cols + TPB - 1) / TPB), (unsigned)n_rows, 1);
+    const dim3 grid((unsigned)((n_cols + TPB - 1) / TPB), (unsigned)((n_rows + INIT_DT_ROWS - 1) / INIT_DT_ROWS), 1);
     if (s->d.tc.eos == ARMON_EOS_BIZARRIUM)
         k_init_dt<ARMON_EOS_BIZARRIUM><<<grid, TPB, 0, s->ctx->stream>>>(n_rows, n_cols, pitch, (int)D.g, b[0], b[1],
                                                                          b[2], b[3], s->d.tc.gamma, s->ts);

@@ -8,12 +8,12 @@
 // head of the chain runs one step ahead of the rest:
 //
 //   stage A (cell a)        : EOS(a), Godunov interface a                       -- uses nothing produced in this step
-//   stage B (one behind)    : GAD flux at interface a-2                         -- uses Godunov states up to a-1 only
-//   stages C-E (two behind) : Lagrangian cell a-4, slopes of cell a-5, advection flux a-5, projection of cell a-6
-//                                                                               -- use fluxes up to a-3 only
+//   stages B-E (one behind) : GAD flux a-2, Lagrangian cell a-3, slopes of cell a-4, advection flux a-4,
+//                             projection of cell a-5                            -- use Godunov states up to a-1 only
 //
-// so that the scheduler always has three independent chains to interleave (A2_SKEW = 0 keeps B-E together, one step
-// behind A).  Results of A and B are committed to the register rings at the end of the step.
+// so that the scheduler always has an independent 45-instruction chain to interleave with the other ~260.
+// A2_SKEW = 1 additionally runs stage B one step ahead of C-E (three chains; measured slower: 252 registers).
+// Results of the stages that run ahead are committed to the register rings at the end of the step.
 // Registers: the skew costs one more live slot of (ua, p, rho*c, rho*dx, Godunov state); to pay for it the values that
 // merely ride along the pipeline are left in shared memory instead: ut and E of a cell are re-read from the input ring
 // when the Lagrangian update (3 steps later) and the projection (5 steps later) need them, and the sound speed goes

@@ -271,8 +271,11 @@ def run_gpu_arm(args):
     achieved = BYTES_PER_CELL_SWEEP * local_cells / avg_sweep_s / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic.get("bytes_per_launch") if traffic else None,
-                "peak_source": peak_src, "kernel": f"sweep_{os.environ.get('ARMON_B200_KERNEL', 'async')}_kernel<{args.math}, GAD+minmod, euler_2nd, "
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/sweep_traffic.json), only quoted
+                # for the workload it was captured on
+                "traffic": traffic.get("bytes_per_launch") if traffic and traffic.get("cells_per_launch") == local_cells
+                and w["test"] == "Sod_circ" else None,
+                "peak_source": peak_src, "kernel": f"sweep_{os.environ.get('ARMON_B200_KERNEL', 'async2')}_kernel<{args.math}, GAD+minmod, euler_2nd, "
                           f"{'bizarrium' if w['test'] == 'Bizarrium' else 'perfect gas'}>",
                 "avg_launch_ms": avg_sweep_s * 1e3, "launches_timed": int(sweep_n.value),
                 "algorithmic_bytes_per_launch": BYTES_PER_CELL_SWEEP * local_cells,

@@ -40,8 +40,10 @@ def main():
         rd = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]]
         wr = float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
         with open(sys.argv[sys.argv.index("--traffic") + 1], "w") as f:
+            cells = int(sys.argv[sys.argv.index("--cells") + 1]) if "--cells" in sys.argv else 8192 * 8192
             json.dump({"kernel": d["Kernel Name"], "grid": d["Grid Size"], "dram_bytes_read": rd, "dram_bytes_write": wr,
-                       "bytes_per_launch": rd + wr, "source": rep.split("/")[-1],
+                       "bytes_per_launch": rd + wr, "cells_per_launch": cells, "algorithmic_bytes_per_launch": 64 * cells,
+                       "source": rep.split("/")[-1],
                        "note": "ncu --set full --clock-control none, one launch of the sweep kernel at 8192x8192"}, f, indent=1)
 
 
