@@ -154,7 +154,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -343,11 +343,31 @@ def run_gpu_arm(args):
         "host_wall_ms_per_step": t_host / args.steps * 1e3,
         "final_state": {"cycle": int(st.cycle), "time": st.time, "dt": st.current_dt},
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Library chatter on fd 1 (NCCL prints its version banner there) goes to stderr: stdout carries the JSON line only."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    out = _REAL_STDOUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -65,3 +65,11 @@ def test_nccl_four_gpus_equal_one_gpu_bitwise():
     if n < 4:
         pytest.skip(f"needs >= 4 GPUs, found {n}")
     launch("gpu", 4, extra=("--quick",), timeout=400)
+
+
+@pytest.mark.gpu
+def test_nccl_eight_gpus_equal_one_gpu_bitwise():
+    n = _gpu_count()
+    if n < 8:
+        pytest.skip(f"needs 8 GPUs, found {n}")
+    launch("gpu", 8, extra=("--quick",), timeout=400)
