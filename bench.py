@@ -370,7 +370,9 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200,
+                    help="cycles in the timed region (a real run is thousands of cycles; the one-off h2d/d2h of the fields in the "
+                         "e2e leg is amortised over them)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sod_circ_8192", choices=sorted(WORKLOADS))
