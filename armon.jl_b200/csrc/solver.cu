@@ -342,10 +342,13 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         return seg;
     }
     // as long as possible (8 warm-up rows per segment are redundant work) while keeping >= 6 waves of CTAs
-    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB, ctas_per_sm = s->use_ws ? 7 : 2;   // TMA_TPB == SWEEP_TPB
+    // TMA_TPB == SWEEP_TPB; the async kernels run 8 warps per SM whatever their CTA size
+    const bool async_pitch_ok = s->use_async && ((nw + 2 * s->d.dims.g) % 2) == 0;
+    const long long cols_per_cta = s->use_ws ? 32 : (async_pitch_ok ? ASYNC_TPB : SWEEP_TPB);
+    const long long ctas_per_sm = s->use_ws ? 7 : (async_pitch_ok ? 256 / ASYNC_TPB : 2);
     const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
     const long long want = 6LL * ctas_per_sm * s->ctx->sm_count;
-    const int cands[] = {512, 256, 128, 64, 32, 16};
+    const int cands[] = {2048, 1024, 512, 256, 128, 64, 32, 16};
     for (int seg : cands) {
         if (seg > nm && seg != 16) continue;
         if (ncol * ((nm + seg - 1) / seg) >= want) return seg;
@@ -399,7 +402,8 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         ARMON_LAUNCH_CHECK(s->ctx);
     }
 
-    const long long cols_per_cta = s->use_ws ? 32 : SWEEP_TPB;
+    const bool async_launch = s->use_async && (A.pitch_in % 2) == 0;
+    const long long cols_per_cta = s->use_ws ? 32 : (async_launch ? ASYNC_TPB : SWEEP_TPB);
     const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profile) {
@@ -427,7 +431,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
             ARMON_LAUNCH_CHECK(s->ctx);
         }
         s->sweep_index++;
-    } else if (s->use_async && (A.pitch_in % 2) == 0) {
+    } else if (async_launch) {
         s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->async_smem, s->ctx->stream>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
     } else if (s->use_tma && (A.pitch_in % 2) == 0) {

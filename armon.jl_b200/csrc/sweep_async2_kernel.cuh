@@ -213,7 +213,7 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
 }
 
 #ifndef ASYNC2_MIN_BLOCKS
-#define ASYNC2_MIN_BLOCKS 2
+#define ASYNC2_MIN_BLOCKS (256 / ASYNC_TPB_VALUE)   // 8 warps per SM
 #endif
 
 template <class R, int DIV, int RL, int PROJ, int EOS, int TR>

@@ -20,7 +20,10 @@
 #ifndef ASYNC_NS
 #define ASYNC_NS 8          // ring slots per warp; rows in flight = ASYNC_NS - 1
 #endif
-constexpr int ASYNC_TPB = 128;
+#ifndef ASYNC_TPB_VALUE
+#define ASYNC_TPB_VALUE 128
+#endif
+constexpr int ASYNC_TPB = ASYNC_TPB_VALUE;   // threads (= columns) per CTA; warps are independent of one another
 
 struct AsyncWarpShared {
     double ring[ASYNC_NS][4][32];                          // [slot][variable][lane]
@@ -51,7 +54,7 @@ __device__ __forceinline__ void async_issue_row(const AsyncLane &L, long long of
 }
 
 #ifndef ASYNC_MIN_BLOCKS
-#define ASYNC_MIN_BLOCKS 2
+#define ASYNC_MIN_BLOCKS (256 / ASYNC_TPB_VALUE)   // 8 warps per SM
 #endif
 
 // TR: 1 = the output is written transposed (through the staging tile), 0 = in the layout it was read (A.transpose_out

@@ -144,6 +144,38 @@ def test_march_segment_does_not_change_results(seg, variant):
     g0.close(); g1.close()
 
 
+@pytest.mark.parametrize("N", [(4, 4), (5, 33), (8, 12), (33, 6), (130, 4)])
+def test_tiny_and_ragged_grids_bit_exact(N):
+    """Edge cases of the marching kernels: sub-domains as small as the ghost width (src/parameters.jl:684-690),
+    fewer cells than a warp / a staging chunk / the prefetch lead, odd and even pitches."""
+    kw = dict(N=N, maxcycle=7)
+    stats, grid = run_gpu(reference_params("Sod_circ", **kw))
+    orc = OracleSolver(reference_params("Sod_circ", **kw), "strict", nthreads=1)
+    _, dt, ncyc, err = orc.time_loop()
+    assert err == 0 and stats.cycles == ncyc and stats.last_dt == dt   # tiny grids reach maxtime before 7 cycles
+    for var in ("rho", "u", "v", "E", "p"):
+        assert_same(grid.real(var), orc.real(var), f"{N} {var}")
+    grid.close()
+
+
+def test_fast_mode_large_grid_tracks_strict_mode():
+    """Size-independent property at a grid larger than L2: the fast arithmetic mode stays within 1e-12 (of field
+    scale) of the bit-exact mode, and conserves mass and energy like it."""
+    kw = dict(N=(2048, 1536), maxcycle=25)
+    ps, pf = reference_params("Sod_circ", **kw), reference_params("Sod_circ", math_mode="fast", **kw)
+    gs, gf = armon.BlockGrid(ps), armon.BlockGrid(pf)
+    armon.init_test(ps, gs); armon.init_test(pf, gf)
+    m0, e0 = armon.conservation_vars(pf, gf)
+    armon.time_loop(ps, gs); armon.time_loop(pf, gf)
+    m1, e1 = armon.conservation_vars(pf, gf)
+    assert abs(m0 - m1) <= 1e-11 and abs(e0 - e1) <= 1e-11
+    assert gs.global_dt.cycle == gf.global_dt.cycle == 25
+    assert abs(gs.global_dt.current_dt - gf.global_dt.current_dt) <= 1e-12 * gs.global_dt.current_dt
+    for var in ("rho", "u", "v", "E"):
+        assert scaled_max_diff(gf.real(var), gs.real(var)) <= 1e-12, var
+    gs.close(); gf.close()
+
+
 def test_cst_dt():
     kw = dict(N=(80, 80), cst_dt=True, Dt=1e-3, maxcycle=10)
     stats, grid = run_gpu(reference_params("Sod", **kw))
