@@ -315,3 +315,27 @@ def test_strict_mode_handles_tiny_operands_like_ieee():
         assert_same(g_ws.real(var), g_ieee.real(var), var + " (ws + fix-up kernel)")
     assert g_strict.time_state().current_dt == g_ieee.time_state().current_dt == g_ws.time_state().current_dt
     g_strict.close(); g_ws.close(); g_ieee.close()
+
+
+# ---- 7. output format (src/io.jl:4-43): the file the reference's own comparison tooling reads -------------------
+def test_output_file_round_trip(tmp_path, golden):
+    from armon_jl_b200.io import read_data_from_file
+    test = "Sod"
+    params = reference_params(test, write_output=True, output_dir=str(tmp_path), output_file="out", return_data=True)
+    stats = armon.armon(params)
+    path = tmp_path / "out"
+    text = path.read_text()
+    lines = text.split("\n")
+    assert len([ln for ln in lines if ln.strip()]) == 100 * 100
+    assert lines[100] == "" and lines[99] != ""                       # blank line after each grid row (gnuplot pm3d)
+    first = lines[0].split(", ")
+    assert len(first) == 6 and all(len(tok) == 24 for tok in first)   # "%#24.17e" x 6 saved_vars
+    with open(path) as f:
+        data = read_data_from_file(params, f)
+    ref = golden(test)
+    for var in ("rho", "u", "v", "p"):
+        assert np.array_equal(data[var], stats.data.real(var)), var   # 17 significant digits round-trip exactly
+        assert count_differences(data[var], ref[var]) == 0, var
+    for var in ("x", "y"):
+        assert np.allclose(data[var], ref[var], rtol=0, atol=1e-15), var
+    stats.data.close()
