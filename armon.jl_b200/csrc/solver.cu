@@ -239,12 +239,16 @@ struct armon_solver {
     long long         host_cycle = 0;          // cycles enqueued since the last reset
     bool              started = false;         // initial time step enqueued
     cudaEvent_t       ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t       ev_state = nullptr, ev_halo = nullptr;   // compute -> comm (state ready), comm -> compute (ghosts ready)
+    cudaStream_t      edge_stream = nullptr;                   // the two edge segments of an overlapped sweep
+    cudaEvent_t       ev_edge = nullptr;                       // edge segments done
     bool              timed = false;
     uint64_t          sweep_launches = 0;
     sweep_fn_t        kernel = nullptr;
     // warp-specialised path (sweep_ws_kernel.cuh): main kernel + IEEE fix-up kernel (strict mode only)
     sweep_ws_fn_t     ws_kernel = nullptr, fixup_kernel = nullptr;
     bool              use_ws = false;
+    bool              overlap = true;      // interior / edge split of a sweep around the halo exchange (ARMON_B200_OVERLAP=0 disables)
     // TMA-staged marching kernel (sweep_tma_kernel.cuh); falls back to `kernel` per launch when the bulk-copy
     // alignment rules do not hold (odd input pitch)
     sweep_fn_t        tma_kernel = nullptr;
@@ -306,7 +310,7 @@ int ensure_layout(armon_solver *s, int axis)
 // innermost real rows are sent, the g ghost rows received (translation, same orientation as the reference's
 // pack_to_array!/unpack_from_array!, src/halo_exchange.jl:187-216).  Only rho, u, v, E travel: p, c, g are
 // recomputed by the receiver from the same values, bit for bit.
-int halo_exchange(armon_solver *s, int axis)
+int halo_exchange(armon_solver *s, int axis, cudaStream_t stream)
 {
     const armon_dims &D = s->d.dims;
     const int lo_side = axis == ARMON_AXIS_X ? ARMON_SIDE_LEFT : ARMON_SIDE_BOTTOM;
@@ -323,15 +327,32 @@ int halo_exchange(armon_solver *s, int axis)
     for (int k = 0; k < 4; k++) {
         double *a = s->buf[s->cur][k];
         if (lo >= 0) {
-            ARMON_NCCL(ncclSend(a + D.g * pitch, count, ncclDouble, lo, s->ctx->comm, s->ctx->stream));
-            ARMON_NCCL(ncclRecv(a, count, ncclDouble, lo, s->ctx->comm, s->ctx->stream));
+            ARMON_NCCL(ncclSend(a + D.g * pitch, count, ncclDouble, lo, s->ctx->comm, stream));
+            ARMON_NCCL(ncclRecv(a, count, ncclDouble, lo, s->ctx->comm, stream));
         }
         if (hi >= 0) {
-            ARMON_NCCL(ncclSend(a + nm * pitch, count, ncclDouble, hi, s->ctx->comm, s->ctx->stream));
-            ARMON_NCCL(ncclRecv(a + (nm + D.g) * pitch, count, ncclDouble, hi, s->ctx->comm, s->ctx->stream));
+            ARMON_NCCL(ncclSend(a + nm * pitch, count, ncclDouble, hi, s->ctx->comm, stream));
+            ARMON_NCCL(ncclRecv(a + (nm + D.g) * pitch, count, ncclDouble, hi, s->ctx->comm, stream));
         }
     }
     ARMON_NCCL(ncclGroupEnd());
+    return ARMON_OK;
+}
+
+// Every NCCL call of the solver goes to the context's communication stream, fenced by events on both sides: the
+// compute stream's work so far is visible to it (ev_state), and the compute stream continues after it when
+// `wait_after` (else the caller waits on ev_halo itself, after launching the work that overlaps the exchange).
+int comm_begin(armon_solver *s)
+{
+    ARMON_CUDA(cudaEventRecord(s->ev_state, s->ctx->stream));
+    ARMON_CUDA(cudaStreamWaitEvent(s->ctx->comm_stream, s->ev_state, 0));
+    return ARMON_OK;
+}
+
+int comm_end(armon_solver *s, bool wait_after)
+{
+    ARMON_CUDA(cudaEventRecord(s->ev_halo, s->ctx->comm_stream));
+    if (wait_after) ARMON_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->ev_halo, 0));
     return ARMON_OK;
 }
 
@@ -359,7 +380,6 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
 int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle, int next_axis)
 {
     if (int rc = ensure_layout(s, axis)) return rc;
-    if (int rc = halo_exchange(s, axis)) return rc;
 
     const armon_dims &D = s->d.dims;
     const armon_test_case &tc = s->d.tc;
@@ -391,20 +411,20 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     A.ts = s->ts;
     A.acc_slot = last_of_cycle ? 0 : 1;
 
-    if (A.mirror_lo || A.mirror_hi) {
-        BcFillArgs B;
-        B.rho = const_cast<double *>(A.in[0]); B.ua = const_cast<double *>(A.in[1]);
-        B.ut = const_cast<double *>(A.in[2]); B.E = const_cast<double *>(A.in[3]);
-        B.nm = A.nm; B.nw = A.nw; B.pitch = A.pitch_in; B.g = A.g; B.lo = A.mirror_lo; B.hi = A.mirror_hi;
-        B.fa_lo = A.bc_a_lo; B.ft_lo = A.bc_t_lo; B.fa_hi = A.bc_a_hi; B.ft_hi = A.bc_t_hi;
-        const dim3 bgrid((unsigned)((A.nw + TPB - 1) / TPB), (unsigned)A.g, 2);
-        k_bc_fill<<<bgrid, TPB, 0, s->ctx->stream>>>(B);
-        ARMON_LAUNCH_CHECK(s->ctx);
+    // block_ghost_exchange with the neighbour ranks (src/halo_exchange.jl:286-354) runs on the communication stream.
+    // Only the first and the last march segment read ghost rows: the interior segments are launched right away and
+    // overlap the exchange, the two edge segments follow once the ghost rows have arrived.
+    const long long nseg = (A.nm + A.seg - 1) / A.seg;
+    const bool has_nb = !A.mirror_lo || !A.mirror_hi;
+    const bool overlap = has_nb && nseg >= 3 && s->overlap;
+    if (has_nb) {
+        if (int rc = comm_begin(s)) return rc;
+        if (int rc = halo_exchange(s, axis, s->ctx->comm_stream)) return rc;
+        if (int rc = comm_end(s, !overlap)) return rc;
     }
 
     const bool async_launch = s->use_async && (A.pitch_in % 2) == 0;
     const long long cols_per_cta = s->use_ws ? 32 : (async_launch ? ASYNC_TPB : SWEEP_TPB);
-    const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)((A.nm + A.seg - 1) / A.seg), 1);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profile) {
         if (s->prof_used + 2 > s->prof_events.size()) {
@@ -419,27 +439,58 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         s->prof_used += 2;
         ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
     }
-    if (s->use_ws) {
-        FixupArgs F;
-        F.count = s->fix_count + (s->sweep_index & 1);
-        F.count_next = s->fix_count + ((s->sweep_index + 1) & 1);
-        F.list = s->fix_list;
-        s->ws_kernel<<<grid, WS_TPB, 0, s->ctx->stream>>>(A, F);
+    FixupArgs F;
+    F.count = s->fix_count + (s->sweep_index & 1);
+    F.count_next = s->fix_count + ((s->sweep_index + 1) & 1);
+    F.list = s->fix_list;
+    // one launch over `ny` march segments y_base, y_base + y_jump, ...
+    auto launch = [&](int y_base, int y_jump, long long ny, cudaStream_t st) -> int {
+        A.y_base = y_base;
+        A.y_jump = y_jump;
+        const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
+        if (s->use_ws)
+            s->ws_kernel<<<grid, WS_TPB, 0, st>>>(A, F);
+        else if (async_launch)
+            s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->async_smem, st>>>(A);
+        else if (s->use_tma && (A.pitch_in % 2) == 0)
+            s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), st>>>(A);
+        else
+            s->kernel<<<grid, SWEEP_TPB, 0, st>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
+        return ARMON_OK;
+    };
+    auto bc_fill = [&](cudaStream_t st) -> int {
+        if (!(A.mirror_lo || A.mirror_hi)) return ARMON_OK;
+        BcFillArgs B;
+        B.rho = const_cast<double *>(A.in[0]); B.ua = const_cast<double *>(A.in[1]);
+        B.ut = const_cast<double *>(A.in[2]); B.E = const_cast<double *>(A.in[3]);
+        B.nm = A.nm; B.nw = A.nw; B.pitch = A.pitch_in; B.g = A.g; B.lo = A.mirror_lo; B.hi = A.mirror_hi;
+        B.fa_lo = A.bc_a_lo; B.ft_lo = A.bc_t_lo; B.fa_hi = A.bc_a_hi; B.ft_hi = A.bc_t_hi;
+        const dim3 bgrid((unsigned)((A.nw + TPB - 1) / TPB), (unsigned)A.g, 2);
+        k_bc_fill<<<bgrid, TPB, 0, st>>>(B);
+        ARMON_LAUNCH_CHECK(s->ctx);
+        return ARMON_OK;
+    };
+    if (overlap) {
+        // interior segments on the compute stream, overlapping the exchange; the two edge segments on their own stream
+        // once the ghost rows are there (ev_halo also carries ev_state: the input state is complete), so that they
+        // fill the last, partial wave of the interior launch instead of running after it
+        if (int rc = launch(1, 1, nseg - 2, s->ctx->stream)) return rc;
+        ARMON_CUDA(cudaStreamWaitEvent(s->edge_stream, s->ev_halo, 0));
+        if (int rc = bc_fill(s->edge_stream)) return rc;
+        if (int rc = launch(0, (int)(nseg - 1), 2, s->edge_stream)) return rc;
+        ARMON_CUDA(cudaEventRecord(s->ev_edge, s->edge_stream));
+        ARMON_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->ev_edge, 0));
+    } else {
+        if (int rc = bc_fill(s->ctx->stream)) return rc;
+        if (int rc = launch(0, 1, nseg, s->ctx->stream)) return rc;
+    }
+    if (s->use_ws) {
         if (s->fixup_kernel) {
             s->fixup_kernel<<<2 * s->ctx->sm_count, 32, 0, s->ctx->stream>>>(A, F);
             ARMON_LAUNCH_CHECK(s->ctx);
         }
         s->sweep_index++;
-    } else if (async_launch) {
-        s->async_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->async_smem, s->ctx->stream>>>(A);
-        ARMON_LAUNCH_CHECK(s->ctx);
-    } else if (s->use_tma && (A.pitch_in % 2) == 0) {
-        s->tma_kernel<<<grid, TMA_TPB, TMA_TPB / 32 * sizeof(TmaWarpShared), s->ctx->stream>>>(A);
-        ARMON_LAUNCH_CHECK(s->ctx);
-    } else {
-        s->kernel<<<grid, SWEEP_TPB, 0, s->ctx->stream>>>(A);
-        ARMON_LAUNCH_CHECK(s->ctx);
     }
     if (s->profile) ARMON_CUDA(cudaEventRecord(ev1, s->ctx->stream));
     s->sweep_launches++;
@@ -456,8 +507,10 @@ int allreduce_acc(armon_solver *s)
     if (s->ctx->comm && s->ctx->nranks > 1) {
         // MPI_Iallreduce(MIN) of the local dt (src/utils.jl:126-134, src/solver_state.jl:107-111) becomes an
         // all-reduce(max) of the two CFL maxima: the min of the quotients is the quotient of the max.
+        if (int rc = comm_begin(s)) return rc;
         ARMON_NCCL(ncclAllReduce(&s->ts->acc[0][0], &s->ts->acc[0][0], 2, ncclUint64, ncclMax, s->ctx->comm,
-                                 s->ctx->stream));
+                                 s->ctx->comm_stream));
+        if (int rc = comm_end(s, true)) return rc;
     }
     return ARMON_OK;
 }
@@ -560,6 +613,7 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     armon_solver *s = new armon_solver();
     s->ctx = ctx;
     s->d = *desc;
+    if (const char *ov = getenv("ARMON_B200_OVERLAP")) s->overlap = atoi(ov) != 0;
     const int rl = desc->riemann == ARMON_RIEMANN_GODUNOV ? 0 : 1 + desc->limiter;
     const bool biz = desc->tc.eos == ARMON_EOS_BIZARRIUM;
     if (desc->math_mode == ARMON_MATH_STRICT)
@@ -662,6 +716,10 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     ARMON_CUDA(cudaMalloc(&s->ts, sizeof(DeviceTimeState)));
     ARMON_CUDA(cudaEventCreate(&s->ev_start));
     ARMON_CUDA(cudaEventCreate(&s->ev_stop));
+    ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_state, cudaEventDisableTiming));
+    ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+    ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
+    ARMON_CUDA(cudaStreamCreateWithFlags(&s->edge_stream, cudaStreamNonBlocking));
     k_ts_reset<<<1, 1, 0, ctx->stream>>>(s->ts, desc->cst_dt, desc->Dt);
     ARMON_LAUNCH_CHECK(ctx);
     *out = s;
@@ -678,6 +736,10 @@ int armon_solver_destroy(armon_solver *s)
     if (s->fix_list) cudaFree(s->fix_list);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    if (s->ev_state) cudaEventDestroy(s->ev_state);
+    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+    if (s->ev_edge) cudaEventDestroy(s->ev_edge);
+    if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     delete s;
     return ARMON_OK;
@@ -824,7 +886,9 @@ int armon_solver_halo_exchange(armon_solver *s, int axis)
     if (int rc = solver_check(s)) return rc;
     ARMON_CHECK_ARG(axis == ARMON_AXIS_X || axis == ARMON_AXIS_Y, "axis");
     if (int rc = ensure_layout(s, axis)) return rc;
-    return halo_exchange(s, axis);
+    if (int rc = comm_begin(s)) return rc;
+    if (int rc = halo_exchange(s, axis, s->ctx->comm_stream)) return rc;
+    return comm_end(s, true);
 }
 
 int armon_solver_elapsed_ms(armon_solver *s, float *ms)

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
 
     const long long w = (long long)blockIdx.x * ASYNC_TPB + threadIdx.x;
     const long long w0 = (long long)blockIdx.x * ASYNC_TPB + (threadIdx.x & ~31);
-    const long long m0 = (long long)blockIdx.y * A.seg;
+    const long long m0 = sweep_segment_index(A) * A.seg;
     const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
 
     SweepThread T;

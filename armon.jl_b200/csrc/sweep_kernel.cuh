@@ -43,6 +43,7 @@ struct SweepArgs {
     long long pitch_out;    // transposed output: nm + 2g, else nw + 2g
     int g;
     int seg;                // outputs per march segment, multiple of SWEEP_CHUNK
+    int y_base, y_jump;     // march segment handled by a CTA = y_base + blockIdx.y * y_jump (interior / edge launches)
     int transpose_out;
     int mirror_lo, mirror_hi;   // 1: global edge (ghost rows written by k_bc_fill); 0: ghost rows hold the neighbour's cells
     double bc_a_lo, bc_t_lo, bc_a_hi, bc_t_hi;   // velocity factors of boundary_condition(test, side), used by k_bc_fill
@@ -53,6 +54,14 @@ struct SweepArgs {
     DeviceTimeState *ts;
     int acc_slot;
 };
+
+// index of the march segment of this CTA: a sweep is one launch over all segments, or -- when the ghost rows of a
+// side are still in flight from a neighbour rank -- an interior launch (segments 1 .. n-2) that overlaps the halo
+// exchange and an edge launch (segments 0 and n-1) after it
+__device__ __forceinline__ long long sweep_segment_index(const SweepArgs &A)
+{
+    return (long long)A.y_base + (long long)blockIdx.y * A.y_jump;
+}
 
 // exact s*x for s = sign(src) in {-1, +1}: flip the sign bit of x when src is negative
 __device__ __forceinline__ double flip_sign_by(double x, double src)
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(SWEEP_TPB, SWEEP_MIN_BLOCKS) sweep_kernel(cons
 
     const long long w = (long long)blockIdx.x * SWEEP_TPB + threadIdx.x;
     const long long w0 = (long long)blockIdx.x * SWEEP_TPB + (threadIdx.x & ~31);
-    const long long m0 = (long long)blockIdx.y * A.seg;
+    const long long m0 = sweep_segment_index(A) * A.seg;
     const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
 
     SweepThread T;

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(WS_TPB, WS_MIN_BLOCKS) sweep_ws_kernel(const S
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long w0 = (long long)blockIdx.x * 32;
     const long long w = w0 + lane;
-    const long long m0 = (long long)blockIdx.y * A.seg;
+    const long long m0 = sweep_segment_index(A) * A.seg;
     const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
 
     SweepThread T;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(WS_TPB, WS_MIN_BLOCKS) sweep_ws_kernel(const S
             bad = T.flag.bad() || S.pflag[lane] != 0u;
             if (bad && T.valid) {
                 const unsigned e = atomicAdd(F.count, 1u);
-                F.list[e] = ((unsigned long long)blockIdx.y << 32) | (unsigned long long)(unsigned)w;
+                F.list[e] = ((unsigned long long)sweep_segment_index(A) << 32) | (unsigned long long)(unsigned)w;
             }
         }
         unsigned long long am = bad ? 0ULL : T.amax, tm = bad ? 0ULL : T.tmax;
