@@ -647,10 +647,13 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                 s->use_tma = true;
             }
         }
-        const bool want_async2 = !s->use_tma && (env ? (std::string(env) == "async2" || std::string(env) == "auto")
-                                                     : (desc->kernel_variant == 5 || desc->kernel_variant == 0));
-        const bool want_async = !s->use_tma && (want_async2 || (env ? (std::string(env) == "async")
-                                                                   : (desc->kernel_variant == 4)));
+        // auto: the software-pipelined kernel for the fast mode (0.96 vs 1.03 ms per sweep at 8192^2); the strict mode is
+        // register-bound (255 registers either way) and measures the same or better without the skew (1.92 ms)
+        const bool is_auto = env ? std::string(env) == "auto" : desc->kernel_variant == 0;
+        const bool want_async2 = !s->use_tma && ((env ? std::string(env) == "async2" : desc->kernel_variant == 5) ||
+                                                 (is_auto && desc->math_mode == ARMON_MATH_FAST));
+        const bool want_async = !s->use_tma && (want_async2 || (env ? std::string(env) == "async" : desc->kernel_variant == 4) ||
+                                                (is_auto && desc->math_mode != ARMON_MATH_FAST));
         if (want_async && desc->math_mode != ARMON_MATH_IEEE) {
             bool ok = true;
             s->async_smem = ASYNC_TPB / 32 * (want_async2 ? sizeof(Async2WarpShared) : sizeof(AsyncWarpShared));

@@ -43,6 +43,7 @@ template <class R> struct Pipe2 {
     R Fu[4], Fp[4], FpFu[4];                                // flux used (GAD or Godunov) of interfaces a-2, a-3, and p*u
     R disp[4];                                              // dt * Fu of interfaces a-2 .. a-5
     R dxl[4], Lr[4], Lu[4], LE[4], Lru[4], Lrt[4], LrE[4];  // Lagrangian cells a-3 .. a-5
+    R rdxl[4];                                              // fast mode: 1 / dxl of the same cells (reused by the remap)
     R Ar, Aru, Art, ArE;                                    // advection flux of the previous interface
     R Sr, Sru, Srt, SrE, S2b, S2r;                          // slopes, 2*dxl and its reciprocal of cell a-5
 };
@@ -97,8 +98,14 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
             r_up = limiter<R, LIM>(D::div(u_im - P.Gu[Z3], (u_i - us_i) + R(1e-6), f));
             r_pp = limiter<R, LIM>(D::div(p_im - P.Gp[Z3], (p_i - ps_i) + R(1e-6), f));
         }
-        const R Dm = (P.cdm[Z3] + P.cdm[Z2]) * R(0.5);                                   // (dm_l + dm_r) / 2
-        const R theta = R(0.5) * (R(1.) - ((P.crc[Z3] + P.crc[Z2]) * R(0.5)) * D::div(dt, Dm, f));
+        R theta;
+        if (DIV == DIV_FAST) {   // 0.5 * (1 - (a/2) * (dt / (d/2))) == 0.5 - 0.5 * dt * a / d : 7 operations instead of 11
+            const double a_ = P.crc[Z3].v + P.crc[Z2].v, d_ = P.cdm[Z3].v + P.cdm[Z2].v;
+            theta = R(fma(a_ * (-0.5 * dt.v), rcp_fast(d_), 0.5));
+        } else {
+            const R Dm = (P.cdm[Z3] + P.cdm[Z2]) * R(0.5);                               // (dm_l + dm_r) / 2
+            theta = R(0.5) * (R(1.) - ((P.crc[Z3] + P.crc[Z2]) * R(0.5)) * D::div(dt, Dm, f));
+        }
         B_Fu = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
         B_Fp = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
     }
@@ -113,7 +120,14 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         const R dxl = dx + dt * (P.Fu[ZLn] - P.Fu[ZL]);
         const R dm = P.cdm[ZL];
         const R dtdm = D::div(dt, dm, f);
-        const R Lr = D::div(dm, dxl, f);
+        R Lr;
+        if (DIV == DIV_FAST) {
+            const double r_ = rcp_fast(dxl.v);
+            P.rdxl[ZL] = R(r_);
+            Lr = R(dm.v * r_);
+        } else {
+            Lr = D::div(dm, dxl, f);
+        }
         const R Lu = P.cu[ZL] + dtdm * (P.Fp[ZL] - P.Fp[ZLn]);
         const R LE = R(rowL[96]) + dtdm * (P.FpFu[ZL] - P.FpFu[ZLn]);
         const R Lt(rowL[64]);
@@ -132,7 +146,9 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
             const R two_dxl = R(2.) * dxl_0;
             const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
             const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
-            const typename D::Rcp k2 = D::prepare(two_dxl, f);
+            typename D::Rcp k2;
+            if (DIV == DIV_FAST) { k2.b = two_dxl.v; k2.r = 0.5 * P.rdxl[ZC].v; }   // 1 / (2 dxl) from the Lagrangian stage
+            else k2 = D::prepare(two_dxl, f);
             const R sr = slope_minmod_fused<R>(P.Lr[ZM], P.Lr[ZC], P.Lr[ZP], r_m, r_p);
             const R sru = slope_minmod_fused<R>(P.Lru[ZM], P.Lru[ZC], P.Lru[ZP], r_m, r_p);
             const R srt = slope_minmod_fused<R>(P.Lrt[ZM], P.Lrt[ZC], P.Lrt[ZP], r_m, r_p);
@@ -166,9 +182,8 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         R t_ru = dXr * P.Lu[ZM] - (Anru - P.Aru);
         R t_rt = dXr * Lt - (Anrt - P.Art);
         R t_rE = dXr * P.LE[ZM] - (AnrE - P.ArE);
-        if (DIV == DIV_FAST) {   // the refined reciprocal of a power of two is exact: no need to tell the cases apart
-            const R idx(inv_dx.r);
-            t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
+        if (DIV == DIV_FAST) {
+            // u = (t_ru / dx) / (t_r / dx) = t_ru / t_r: only the density needs the 1/dx factor
         } else if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
             const R idx(A.inv_dx);
             t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
@@ -178,6 +193,7 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         }
         const typename D::Rcp inv_r = D::prepare(t_r, f);
         const R o_ua = D::quot(t_ru, inv_r, f), o_ut = D::quot(t_rt, inv_r, f), o_E = D::quot(t_rE, inv_r, f);
+        if (DIV == DIV_FAST) t_r = t_r * R(inv_dx.r);
         const long long m = a - 5 - q;
         const bool store = T.valid && m < m1;
         {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored contribute 0
@@ -278,8 +294,10 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         async_issue_row(L, march_row_offset(A, a_begin + s), s);
         async_commit();
     }
-    long long off_run = march_row_offset(A, a_begin + LEAD);   // offset of row a + LEAD
-    const long long off_max = (A.nm + 2 * A.g - 1) * A.pitch_in;
+    // rows past the last array row (tail of the last segment) are not fetched: their slots keep older, finite rows,
+    // which only feed cells that are never emitted
+    long long off_run = (a_begin + LEAD + A.g) * A.pitch_in;            // offset of row a + LEAD
+    int rows_left = (int)((A.nm + A.g - 1) - (a_begin + LEAD));         // >= 0 while row a + LEAD exists
 
     const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
     Pipe2<R> P;
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.);
         P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
         P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.LE[j] = R(1.);
-        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.);
+        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.); P.rdxl[j] = R(1.);
     }
     P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
     P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
@@ -303,9 +321,9 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
     {                                                                                                       \
         async_wait<LEAD - 1>();                                                                             \
         __syncwarp();   /* every lane's copies of row a have landed; the slot refilled below was last read a step ago */ \
-        async_issue_row(L, off_run, (int)((step + LEAD) & (A2_NS - 1)));                                    \
+        async_issue_row(L, off_run, (int)((step + LEAD) & (A2_NS - 1)), rows_left >= 0);                    \
         async_commit();                                                                                     \
-        off_run = off_run < off_max ? off_run + A.pitch_in : off_run;   /* clamped at the last array row */ \
+        off_run += A.pitch_in; rows_left--;                                                                 \
         march_compute2<R, DIV, RL, PROJ, EOS, J, TR, EMIT>(A, T, P, ring, cring, step, a, dt, inv_dx, KC, m1, stage); \
         a++; step++;                                                                                        \
     }

@@ -45,9 +45,9 @@ struct AsyncLane {
 };
 
 // copies of the array row whose first cell has element offset `off` into ring slot `s`
-__device__ __forceinline__ void async_issue_row(const AsyncLane &L, long long off, int s)
+__device__ __forceinline__ void async_issue_row(const AsyncLane &L, long long off, int s, bool row_ok = true)
 {
-    if (L.active) {
+    if (L.active && row_ok) {
         async_copy16(L.dst[0] + 1024u * (unsigned)s, L.src[0] + off);
         async_copy16(L.dst[1] + 1024u * (unsigned)s, L.src[1] + off);
     }
