@@ -44,8 +44,11 @@ template <class R> struct Pipe2 {
     R disp[4];                                              // dt * Fu of interfaces a-2 .. a-5
     R dxl[4], Lr[4], Lu[4], LE[4], Lru[4], Lrt[4], LrE[4];  // Lagrangian cells a-3 .. a-5
     R rdxl[4];                                              // fast mode: 1 / dxl of the same cells (reused by the remap)
+    R rrho[4];                                              // fast mode: 1 / rho of cells a .. a-3 (EOS reciprocal reused for dt/dm)
     R Ar, Aru, Art, ArE;                                    // advection flux of the previous interface
     R Sr, Sru, Srt, SrE, S2b, S2r;                          // slopes, 2*dxl and its reciprocal of cell a-5
+    R Rsum;                                                 // fast mode: 1 / (dxl[a-5] + dxl[a-4]), shared by two cells
+    R Dr, Dru, Drt, DrE;                                    // fast mode: q[a-4] - q[a-5] of the four remapped quantities
 };
 
 // One skewed march step.  `step` = a - a_begin; J = step & 3 is static.  `ring` / `cring` point at this lane's column
@@ -71,11 +74,12 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
 
     // ---- stage A, cell a: EOS (src/kernels.jl:4-55), Godunov state at interface a (src/riemann_schemes.jl:21-30) ----
     // results are committed to the rings at the end of the step: with q = 1 the slots still hold cell a-4
-    R A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp;
+    R A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp, A_rrho(0.);
     {
         const R rho(row0[0]), ua(row0[32]), ut(row0[64]), E(row0[96]);
         R p, c;
         eos_eval<R, DIV, EOS>(A, rho, ua, ut, E, p, c, f);
+        if (DIV == DIV_FAST) A_rrho = R(rcp_fast(rho.v));   // the very reciprocal the EOS just formed (common subexpression)
         const R rc = rho * c;
         cring[(step & (A2_CS - 1)) * 32] = c.v;
         acoustic_godunov<R, DIV>(P.crc[Z1], rc, P.cu[Z1], ua, P.cp[Z1], p, A_Gu, A_Gp, f);
@@ -119,7 +123,8 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
     {
         const R dxl = dx + dt * (P.Fu[ZLn] - P.Fu[ZL]);
         const R dm = P.cdm[ZL];
-        const R dtdm = D::div(dt, dm, f);
+        const R dtdm = DIV == DIV_FAST ? R((dt.v * inv_dx.r) * P.rrho[ZL].v)   // dt / (rho dx) with the EOS's 1 / rho
+                                       : D::div(dt, dm, f);
         R Lr;
         if (DIV == DIV_FAST) {
             const double r_ = rcp_fast(dxl.v);
@@ -144,15 +149,29 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         if (PROJ == ARMON_PROJ_EULER_2ND) {
             const R dxl_m = P.dxl[ZM], dxl_0 = P.dxl[ZC], dxl_p = P.dxl[ZP];
             const R two_dxl = R(2.) * dxl_0;
-            const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
-            const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
             typename D::Rcp k2;
-            if (DIV == DIV_FAST) { k2.b = two_dxl.v; k2.r = 0.5 * P.rdxl[ZC].v; }   // 1 / (2 dxl) from the Lagrangian stage
-            else k2 = D::prepare(two_dxl, f);
-            const R sr = slope_minmod_fused<R>(P.Lr[ZM], P.Lr[ZC], P.Lr[ZP], r_m, r_p);
-            const R sru = slope_minmod_fused<R>(P.Lru[ZM], P.Lru[ZC], P.Lru[ZP], r_m, r_p);
-            const R srt = slope_minmod_fused<R>(P.Lrt[ZM], P.Lrt[ZC], P.Lrt[ZP], r_m, r_p);
-            const R srE = slope_minmod_fused<R>(P.LrE[ZM], P.LrE[ZC], P.LrE[ZP], r_m, r_p);
+            R sr, sru, srt, srE;
+            if (DIV == DIV_FAST) {
+                // 1 / (dxl_i + dxl_{i+1}) serves r+ of cell i and r- of cell i+1, q_{i+1} - q_i serves both slopes, and
+                // 1 / (2 dxl) comes from the Lagrangian stage: 1 reciprocal and 4 differences per step instead of 3 and 8
+                const double rsum_p = rcp_fast(dxl_0.v + dxl_p.v);
+                const R r_m(two_dxl.v * P.Rsum.v), r_p(two_dxl.v * rsum_p);
+                const R dr = P.Lr[ZP] - P.Lr[ZC], dru = P.Lru[ZP] - P.Lru[ZC], drt = P.Lrt[ZP] - P.Lrt[ZC], drE = P.LrE[ZP] - P.LrE[ZC];
+                sr = minmod_of(r_p * dr, r_m * P.Dr);
+                sru = minmod_of(r_p * dru, r_m * P.Dru);
+                srt = minmod_of(r_p * drt, r_m * P.Drt);
+                srE = minmod_of(r_p * drE, r_m * P.DrE);
+                P.Rsum = R(rsum_p); P.Dr = dr; P.Dru = dru; P.Drt = drt; P.DrE = drE;
+                k2.b = two_dxl.v; k2.r = 0.5 * P.rdxl[ZC].v;
+            } else {
+                const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
+                const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
+                k2 = D::prepare(two_dxl, f);
+                sr = slope_minmod_fused<R>(P.Lr[ZM], P.Lr[ZC], P.Lr[ZP], r_m, r_p);
+                sru = slope_minmod_fused<R>(P.Lru[ZM], P.Lru[ZC], P.Lru[ZP], r_m, r_p);
+                srt = slope_minmod_fused<R>(P.Lrt[ZM], P.Lrt[ZC], P.Lrt[ZP], r_m, r_p);
+                srE = slope_minmod_fused<R>(P.LrE[ZM], P.LrE[ZC], P.LrE[ZP], r_m, r_p);
+            }
 
             const R dxe = rsel(pos, -(dx - P.disp[ZM]), dx + P.disp[ZP]);
             typename D::Rcp ksel;
@@ -196,13 +215,11 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
         if (DIV == DIV_FAST) t_r = t_r * R(inv_dx.r);
         const long long m = a - 5 - q;
         const bool store = T.valid && m < m1;
-        {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored contribute 0
-            unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
-            unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
-            ba = store ? ba : 0ULL;
-            bt = store ? bt : 0ULL;
-            T.amax = ba > T.amax ? ba : T.amax;
-            T.tmax = bt > T.tmax ? bt : T.tmax;
+        {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored do not contribute
+            const unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
+            const unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+            T.amax = (store && ba > T.amax) ? ba : T.amax;   // `store` rides on the predicate input of the compare
+            T.tmax = (store && bt > T.tmax) ? bt : T.tmax;
         }
         if (TR == 1) {
             double *s = stage + (threadIdx.x & 31) * SWEEP_STAGE_PITCH + k_chunk;
@@ -222,6 +239,7 @@ __device__ __forceinline__ void march_compute2(const SweepArgs &A, SweepThread &
 
     // ---- commit the results of the stages that ran ahead (their ring slots were still being read above) ----
     P.cu[Z0] = A_ua; P.cp[Z0] = A_p; P.crc[Z0] = A_rc; P.cdm[Z0] = A_dm; P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
+    if (DIV == DIV_FAST) P.rrho[Z0] = A_rrho;
     if (q == 1) {
         P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu; P.disp[Z2] = B_disp;
     }
@@ -306,10 +324,11 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         P.cu[j] = R(0.); P.cp[j] = R(1.); P.crc[j] = R(1.); P.cdm[j] = R(1.);
         P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
         P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.LE[j] = R(1.);
-        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.); P.rdxl[j] = R(1.);
+        P.Lru[j] = R(0.); P.Lrt[j] = R(0.); P.LrE[j] = R(1.); P.rdxl[j] = R(1.); P.rrho[j] = R(1.);
     }
     P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
     P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
+    P.Rsum = R(0.5); P.Dr = R(0.); P.Dru = R(0.); P.Drt = R(0.); P.DrE = R(0.);
 
     double *stage = S.stage;
     const double *ring = &S.ring[0][0][lane];

@@ -84,6 +84,15 @@ template <class R> __device__ __forceinline__ R slope_minmod_fused(R qm, R q0, R
     return R(sx < 0 ? 0.0 : m);
 }
 
+// the selection part of slope_minmod_fused on already formed limited differences
+template <class R> __device__ __forceinline__ R minmod_of(R d_p, R d_m)
+{
+    const bool m_smaller = fabs(d_m.v) < fabs(d_p.v);
+    const double m = m_smaller ? d_m.v : d_p.v;
+    const int sx = __double2hiint(d_p.v) ^ __double2hiint(d_m.v);
+    return R(sx < 0 ? 0.0 : m);
+}
+
 template <class R, int DIV, int EOS>
 __device__ __forceinline__ void eos_eval(const SweepArgs &A, R rho, R ua, R ut, R E, R &p, R &c, RangeFlag &f)
 {
@@ -257,13 +266,11 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
         const long long m = a - 4;
         const bool store = T.valid && m < m1;
         // dtCFL accumulators (src/reductions.jl:14-20): max(|u+c|,|u-c|) == |u|+c, new velocities, c of this sweep's EOS
-        {   // branch-free: cells that are not stored contribute 0
-            unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
-            unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
-            ba = store ? ba : 0ULL;
-            bt = store ? bt : 0ULL;
-            T.amax = ba > T.amax ? ba : T.amax;
-            T.tmax = bt > T.tmax ? bt : T.tmax;
+        {   // branch-free: cells that are not stored do not contribute
+            const unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
+            const unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+            T.amax = (store && ba > T.amax) ? ba : T.amax;   // `store` rides on the predicate input of the compare
+            T.tmax = (store && bt > T.tmax) ? bt : T.tmax;
         }
         if (STAGED && transpose_out) {
             // stage[var][lane][k]: flushed as rows of SWEEP_CHUNK contiguous doubles by flush_stage()
