@@ -259,6 +259,7 @@ struct armon_solver {
     size_t            async_smem = 0;      // dynamic shared memory per CTA of the selected async kernel
     unsigned         *fix_count = nullptr;            // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
+    unsigned          fix_cap = 0;                    // entries
     uint64_t          sweep_index = 0;
     // optional per-sweep-kernel timing (CUDA events on the launching stream), for the roofline figure
     bool              profile = false;
@@ -440,9 +441,13 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
     }
     FixupArgs F;
-    F.count = s->fix_count + (s->sweep_index & 1);
-    F.count_next = s->fix_count + ((s->sweep_index + 1) & 1);
+    F.count = s->fix_count ? s->fix_count + (s->sweep_index & 1) : nullptr;
+    F.count_next = s->fix_count ? s->fix_count + ((s->sweep_index + 1) & 1) : nullptr;
     F.list = s->fix_list;
+    A.fix_count = F.count;
+    A.fix_list = F.list;
+    A.fix_cap = s->fix_cap;
+    A.fix_rows = (async_launch && s->fixup_kernel) ? FIX_CHUNKS * SWEEP_CHUNK : 0;
     // one launch over `ny` march segments y_base, y_base + y_jump, ...
     auto launch = [&](int y_base, int y_jump, long long ny, cudaStream_t st) -> int {
         A.y_base = y_base;
@@ -485,8 +490,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
         if (int rc = bc_fill(s->ctx->stream)) return rc;
         if (int rc = launch(0, 1, nseg, s->ctx->stream)) return rc;
     }
-    if (s->use_ws) {
+    if (s->use_ws || (async_launch && s->fixup_kernel)) {
         if (s->fixup_kernel) {
+            A.y_base = 0; A.y_jump = 1;
             s->fixup_kernel<<<2 * s->ctx->sm_count, 32, 0, s->ctx->stream>>>(A, F);
             ARMON_LAUNCH_CHECK(s->ctx);
         }
@@ -702,7 +708,9 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
             }
             s->use_ws = s->ws_kernel != nullptr;
         }
-        if (s->use_ws) {
+        if (s->use_async && desc->math_mode == ARMON_MATH_STRICT)
+            s->fixup_kernel = biz ? sweep_fixup_table_biz(rl, desc->projection) : sweep_fixup_table_pg(rl, desc->projection);
+        if (s->use_ws || (s->use_async && s->fixup_kernel)) {
             // work list of the IEEE fix-up: one entry per (column, segment) at most
             long long cap = 0;
             for (int axis = 0; axis < 2; axis++) {
@@ -711,6 +719,14 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                 const long long n = nw * ((nm + seg - 1) / seg);
                 cap = n > cap ? n : cap;
             }
+            if (s->use_async) {
+                // cp.async kernels: one entry per (column, chunk of 8 rows) at most; capped at 32 MB, an overflow (a
+                // domain full of out-of-range values) raises ARMON_ERR_RANGE
+                const long long worst = (D.nx > D.ny ? D.nx : D.ny) * (((D.nx > D.ny ? D.ny : D.nx) + SWEEP_CHUNK - 1) / SWEEP_CHUNK + 1);
+                cap = worst < (4LL << 20) ? worst : (4LL << 20);
+                if (cap < 1024) cap = 1024;
+            }
+            s->fix_cap = (unsigned)cap;
             ARMON_CUDA(cudaMalloc(&s->fix_count, 2 * sizeof(unsigned)));
             ARMON_CUDA(cudaMemsetAsync(s->fix_count, 0, 2 * sizeof(unsigned), ctx->stream));
             ARMON_CUDA(cudaMalloc(&s->fix_list, (size_t)cap * sizeof(unsigned long long)));

@@ -318,6 +318,10 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
     int rows_left = (int)((A.nm + A.g - 1) - (a_begin + LEAD));         // >= 0 while row a + LEAD exists
 
     const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
+    ChunkFix C;
+    C.tot_a = 0ULL; C.tot_t = 0ULL; C.taint = 0;
+    if (DIV == DIV_FLAGGED) range_check_dividend(dt.v, T.flag);
+    C.always = DIV == DIV_FLAGGED && T.flag.bad();
     Pipe2<R> P;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -366,23 +370,13 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC2_MIN_BLOCKS) sweep_async2_ker
         A2_STEP((3 + A2_Q) & 3, 1, kc + 2)
         A2_STEP((4 + A2_Q) & 3, 1, kc + 3)
         if (TR == 1 && (it & 1)) flush_stage(A, stage, w0, a - 13 - A2_Q, m1);
+        if (it & 1) chunk_end<DIV>(A, T, C, a - 13 - A2_Q, w);
     }
 #undef A2_STEP
     async_wait<0>();
 
-    if (DIV == DIV_FLAGGED) {
-        // see sweep_kernel: threads whose operands left the proven range of the branch-free division recompute
-        // their segment with nvcc's full IEEE division (register-prefetch path, direct stores)
-        range_check_dividend(dt.v, T.flag);
-        if (T.flag.bad() && T.valid) {
-            T.amax = 0ULL; T.tmax = 0ULL;
-            march_segment<R, DIV_IEEE, RL, PROJ, EOS, false>(A, T, dt, m0, m1, w0, stage);
-            if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(&A.ts->redo_count, 1u);
-        }
-        __syncwarp();
-    }
-
-    unsigned long long am = T.amax, tm = T.tmax;
+    unsigned long long am = DIV == DIV_FLAGGED ? C.tot_a : T.amax, tm = DIV == DIV_FLAGGED ? C.tot_t : T.tmax;
+    if (!T.valid) { am = 0ULL; tm = 0ULL; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);

@@ -53,6 +53,41 @@ __device__ __forceinline__ void async_issue_row(const AsyncLane &L, long long of
     }
 }
 
+// Strict-mode bookkeeping of the cp.async kernels, evaluated once per chunk of SWEEP_CHUNK emitted cells.  An operand
+// outside the proven range of the branch-free division (common.cuh) met while chunk k is being emitted can only reach
+// cells emitted in chunks k .. k+2 (dependency cone of 9 cells, emission lag <= 5 steps): the thread appends
+// (first row of chunk k, column) to the work list and keeps the CFL maxima of those three chunks out of its totals;
+// sweep_fixup_kernel recomputes FIX_CHUNKS * SWEEP_CHUNK rows of that column with nvcc's full IEEE division afterwards
+// (bit-identical for the cells that were in range), densely packed, one thread per entry.
+constexpr int FIX_CHUNKS = 3;
+struct ChunkFix {
+    unsigned long long tot_a, tot_t;   // CFL maxima over the clean chunks
+    int taint;                         // chunks still reached by an out-of-range operand met earlier
+    bool always;                       // dt or dx themselves are out of range: every chunk goes to the fix-up
+};
+
+template <int DIV>
+__device__ __forceinline__ void chunk_end(const SweepArgs &A, SweepThread &T, ChunkFix &C, long long mb, long long w)
+{
+    if (DIV != DIV_FLAGGED) return;
+    if (T.flag.bad() || C.always) {
+        C.taint = FIX_CHUNKS;
+        if (T.valid) {
+            const unsigned e = atomicAdd(A.fix_count, 1u);
+            if (e < A.fix_cap) A.fix_list[e] = ((unsigned long long)mb << 32) | (unsigned long long)(unsigned)w;
+            else A.ts->error = ARMON_ERR_RANGE;
+        }
+    }
+    if (C.taint > 0) {
+        C.taint--;
+    } else {
+        C.tot_a = T.amax > C.tot_a ? T.amax : C.tot_a;
+        C.tot_t = T.tmax > C.tot_t ? T.tmax : C.tot_t;
+    }
+    T.amax = 0ULL; T.tmax = 0ULL;
+    T.flag = RangeFlag();
+}
+
 #ifndef ASYNC_MIN_BLOCKS
 #define ASYNC_MIN_BLOCKS (256 / ASYNC_TPB_VALUE)   // 8 warps per SM
 #endif
@@ -122,6 +157,10 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
     const long long off_max = (A.nm + 2 * A.g - 1) * A.pitch_in;
 
     const typename Div<R, DIV>::Rcp inv_dx = Div<R, DIV>::prepare(R(A.dx), T.flag);
+    ChunkFix C;
+    C.tot_a = 0ULL; C.tot_t = 0ULL; C.taint = 0;
+    if (DIV == DIV_FLAGGED) range_check_dividend(dt.v, T.flag);
+    C.always = DIV == DIV_FLAGGED && T.flag.bad();
     Pipe<R> P;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -174,23 +213,13 @@ __global__ void __launch_bounds__(ASYNC_TPB, ASYNC_MIN_BLOCKS) sweep_async_kerne
         ASYNC_STEP(2, 1)
         ASYNC_STEP(3, 1)
         if (TR == 1 && (it & 1)) flush_stage(A, stage, w0, a - 12, m1);
+        if (it & 1) chunk_end<DIV>(A, T, C, a - 12, w);
     }
 #undef ASYNC_STEP
     async_wait<0>();
 
-    if (DIV == DIV_FLAGGED) {
-        // see sweep_kernel: threads whose operands left the proven range of the branch-free division recompute
-        // their segment with nvcc's full IEEE division (register-prefetch path, direct stores)
-        range_check_dividend(dt.v, T.flag);
-        if (T.flag.bad() && T.valid) {
-            T.amax = 0ULL; T.tmax = 0ULL;
-            march_segment<R, DIV_IEEE, RL, PROJ, EOS, false>(A, T, dt, m0, m1, w0, stage);
-            if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(&A.ts->redo_count, 1u);
-        }
-        __syncwarp();
-    }
-
-    unsigned long long am = T.amax, tm = T.tmax;
+    unsigned long long am = DIV == DIV_FLAGGED ? C.tot_a : T.amax, tm = DIV == DIV_FLAGGED ? C.tot_t : T.tmax;
+    if (!T.valid) { am = 0ULL; tm = 0ULL; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);

@@ -53,6 +53,12 @@ struct SweepArgs {
     double gamma;
     DeviceTimeState *ts;
     int acc_slot;
+    // strict mode of the cp.async kernels: (segment << 32 | column) of the threads whose operands left the proven range
+    // of the branch-free division; sweep_fixup_kernel recomputes them with nvcc's full IEEE division afterwards
+    unsigned *fix_count;
+    unsigned long long *fix_list;
+    unsigned fix_cap;       // capacity of fix_list (entries); an overflow raises ARMON_ERR_RANGE
+    int fix_rows;           // 0: an entry is (segment << 32 | column); > 0: (first row << 32 | column), fix_rows rows
 };
 
 // index of the march segment of this CTA: a sweep is one launch over all segments, or -- when the ghost rows of a

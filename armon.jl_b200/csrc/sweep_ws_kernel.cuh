@@ -368,15 +368,18 @@ template <class R, int RL, int PROJ, int EOS>
 __global__ void __launch_bounds__(32) sweep_fixup_kernel(const SweepArgs A, const FixupArgs F)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) *F.count_next = 0u;
-    const unsigned count = *F.count;
+    const unsigned raw_count = *F.count;
+    const unsigned count = (A.fix_rows > 0 && raw_count > A.fix_cap) ? A.fix_cap : raw_count;
     const DeviceTimeState *ts = A.ts;
     if (count == 0u || ts->done) return;
     const R dt = R(ts->current_dt) * R(A.dt_factor);
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
         const unsigned long long entry = F.list[e];
-        const long long w = (long long)(entry & 0xffffffffULL), seg = (long long)(entry >> 32);
-        const long long m0 = seg * A.seg;
-        const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
+        const long long w = (long long)(entry & 0xffffffffULL), hi = (long long)(entry >> 32);
+        // ws kernel: the entry names a whole march segment; cp.async kernels: fix_rows rows starting at row `hi`
+        const long long m0 = A.fix_rows > 0 ? hi : hi * A.seg;
+        const long long len = A.fix_rows > 0 ? A.fix_rows : A.seg;
+        const long long m1 = (m0 + len < A.nm) ? m0 + len : A.nm;
         SweepThread T;
         T.valid = true;
         T.col = w + A.g;
