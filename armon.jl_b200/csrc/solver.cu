@@ -28,12 +28,14 @@ __global__ void k_ts_reset(DeviceTimeState *ts, int cst_dt, double Dt)
     ts->done = 0;
     ts->range_error = 0;
     ts->redo_count = 0u;
-    ts->acc[0][0] = ts->acc[0][1] = ts->acc[1][0] = ts->acc[1][1] = 0ULL;
+    for (int k = 0; k < 3; k++) ts->acc[k][0] = ts->acc[k][1] = 0ULL;
 }
 
 struct CycleStepArgs {
     int first;            // 1: called before cycle 0 (no next_cycle! to apply)
-    int acc_is_xy;        // 1: acc[0] = (x, y); 0: acc[0] = (y, x)
+    long long k;          // index of the cycle that just ran (when !first)
+    int read_slot;        // accumulator slot holding the CFL maxima to consume (-1: none, i.e. after cycle 0)
+    int acc_is_xy;        // 1: that slot holds (x, y); 0: (y, x)
     double dx, dy;        // GLOBAL cell sizes, src/reductions.jl:91-94
     double cfl, maxtime;
     long long maxcycle;
@@ -41,53 +43,51 @@ struct CycleStepArgs {
     double Dt;
 };
 
-// next_cycle! (src/solver_state.jl:145-166) of the cycle that just ran, the loop condition of time_loop
-// (src/solver.jl:333), then next_time_step + update_dt! (src/reductions.jl:164-199, src/solver_state.jl:102-142) of the
-// cycle about to run.  SURVEY.md section 3.3 gives the recurrence this reproduces.
+// next_cycle! (src/solver_state.jl:145-166) of the cycle that just ran, next_time_step + update_dt!
+// (src/reductions.jl:164-199, src/solver_state.jl:102-142) and the loop condition of time_loop (src/solver.jl:333).
+// SURVEY.md section 3.3 gives the recurrence this reproduces: D0 = cfl L(0) is used by cycles 0 and 1;
+// D_k = min(cfl L(k), 1.05 D_{k-1}) is used by cycle k+1, where L(k) comes from the state at the start of cycle k, i.e.
+// from the maxima accumulated by the last sweep of cycle k-1.  Like the reference's MPI_Iallreduce (waited one cycle
+// later, src/solver_state.jl:89-119,154-156) the reduction of those maxima has the whole of cycle k to complete: the
+// step after cycle k consumes the slot written by cycle k-1.
 __global__ void k_cycle_step(DeviceTimeState *ts, CycleStepArgs a)
 {
-    const double inf = __longlong_as_double(0x7FF0000000000000LL);
-    const unsigned long long bx = ts->acc[0][a.acc_is_xy ? 0 : 1];
-    const unsigned long long by = ts->acc[0][a.acc_is_xy ? 1 : 0];
-    ts->acc[0][0] = ts->acc[0][1] = ts->acc[1][0] = ts->acc[1][1] = 0ULL;
+    unsigned long long bx = 0ULL, by = 0ULL;
+    if (a.read_slot >= 0) {
+        bx = ts->acc[a.read_slot][a.acc_is_xy ? 0 : 1];
+        by = ts->acc[a.read_slot][a.acc_is_xy ? 1 : 0];
+        ts->acc[a.read_slot][0] = ts->acc[a.read_slot][1] = 0ULL;
+    }
+    ts->acc[2][0] = ts->acc[2][1] = 0ULL;
     if (ts->done) return;
 
     if (!a.first) {
         ts->cycle += 1;
         ts->time = __dadd_rn(ts->time, ts->current_dt);
-        if (a.cst_dt) {
-            ts->current_dt = ts->next_cycle_dt = a.Dt;
-        } else {
-            ts->current_dt = ts->next_cycle_dt;
-            ts->next_cycle_dt = inf;
-        }
     }
-    if (!(ts->time < a.maxtime && ts->cycle < a.maxcycle)) {
-        ts->done = 1;
-        return;
-    }
+    ts->next_cycle_dt = __longlong_as_double(0x7FF0000000000000LL);   // typemax(T) after next_cycle!
     if (a.cst_dt) {   // src/reductions.jl:165-167
         ts->current_dt = a.Dt;
         ts->next_cycle_dt = a.Dt;
-        return;
+    } else if (a.read_slot >= 0) {
+        // local_time_step: min over cells of min(dx/max(|u+c|,|u-c|), dy/...) == min(dx/max_cells(|u|+c), dy/...)
+        // (division by a positive number is monotone, so the min commutes with the correctly rounded quotient)
+        const double ax = __longlong_as_double((long long)bx), ay = __longlong_as_double((long long)by);
+        double new_dt = fmin(__ddiv_rn(a.dx, ax), __ddiv_rn(a.dy, ay));
+        if (ax != ax || ay != ay) new_dt = ax + ay;   // NaN in the fields: propagate
+        const double previous_dt = ts->current_dt;
+        if (!isfinite(new_dt) || new_dt <= 0.0) {   // src/solver_state.jl:123-124
+            ts->error = ARMON_ERR_TIME;
+            ts->done = 1;
+            return;
+        } else if (previous_dt == 0.0) {
+            new_dt = __dmul_rn(a.cfl, new_dt);
+        } else {
+            new_dt = fmin(__dmul_rn(a.cfl, new_dt), __dmul_rn(1.05, previous_dt));
+        }
+        ts->current_dt = new_dt;
     }
-    // local_time_step: min over cells of min(dx/max(|u+c|,|u-c|), dy/...) == min(dx/max_cells(|u|+c), dy/...)
-    // (division by a positive number is monotone, so the min commutes with the correctly rounded quotient)
-    const double ax = __longlong_as_double((long long)bx), ay = __longlong_as_double((long long)by);
-    double new_dt = fmin(__ddiv_rn(a.dx, ax), __ddiv_rn(a.dy, ay));
-    if (ax != ax || ay != ay) new_dt = ax + ay;   // NaN in the fields: propagate
-    const double previous_dt = ts->current_dt;
-    if (!isfinite(new_dt) || new_dt <= 0.0) {   // src/solver_state.jl:123-124
-        ts->error = ARMON_ERR_TIME;
-        ts->done = 1;
-        return;
-    } else if (previous_dt == 0.0) {
-        new_dt = __dmul_rn(a.cfl, new_dt);
-    } else {
-        new_dt = fmin(__dmul_rn(a.cfl, new_dt), __dmul_rn(1.05, previous_dt));
-    }
-    ts->next_cycle_dt = new_dt;
-    if (ts->current_dt == 0.0) ts->current_dt = new_dt;
+    if (!(ts->time < a.maxtime && ts->cycle < a.maxcycle)) ts->done = 1;
 }
 
 // EOS_init + the first local_time_step (src/solver.jl:291-297): CFL maxima of the initial state.
@@ -120,8 +120,8 @@ __global__ void k_init_dt(long long n_rows, long long n_cols, long long pitch, i
         by = oy > by ? oy : by;
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMax(&ts->acc[0][0], bx);
-        atomicMax(&ts->acc[0][1], by);
+        atomicMax(&ts->acc[1][0], bx);   // slot of "cycle -1": consumed by the step before cycle 0
+        atomicMax(&ts->acc[1][1], by);
     }
 }
 
@@ -240,6 +240,8 @@ struct armon_solver {
     bool              started = false;         // initial time step enqueued
     cudaEvent_t       ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t       ev_state = nullptr, ev_halo = nullptr;   // compute -> comm (state ready), comm -> compute (ghosts ready)
+    cudaEvent_t       ev_dt[2] = {nullptr, nullptr};           // all-reduce of accumulator slot 0 / 1 done
+    bool              last_axis_is_x[2] = {true, true};        // axis of the sweep that filled accumulator slot 0 / 1
     cudaStream_t      edge_stream = nullptr;                   // the two edge segments of an overlapped sweep
     cudaEvent_t       ev_edge = nullptr;                       // edge segments done
     bool              timed = false;
@@ -410,7 +412,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     A.dt_factor = dt_factor;
     A.gamma = tc.gamma;
     A.ts = s->ts;
-    A.acc_slot = last_of_cycle ? 0 : 1;
+    A.acc_slot = last_of_cycle ? (int)(s->host_cycle & 1) : 2;
 
     // block_ghost_exchange with the neighbour ranks (src/halo_exchange.jl:286-354) runs on the communication stream.
     // Only the first and the last march segment read ghost rows: the interior segments are launched right away and
@@ -508,23 +510,34 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, bool last_of_cycle
     return ARMON_OK;
 }
 
-int allreduce_acc(armon_solver *s)
+// MPI_Iallreduce(MIN) of the local dt (src/utils.jl:126-134, src/solver_state.jl:107-111) becomes an all-reduce(max) of
+// the two CFL maxima of one accumulator slot (the min of the quotients is the quotient of the max), issued on the
+// communication stream.  `wait`: the compute stream waits for it right away (initial time step); otherwise it is waited
+// one cycle later (wait_allreduce), so that it overlaps the sweeps of the next cycle.
+int allreduce_acc(armon_solver *s, int slot, bool wait)
 {
     if (s->ctx->comm && s->ctx->nranks > 1) {
-        // MPI_Iallreduce(MIN) of the local dt (src/utils.jl:126-134, src/solver_state.jl:107-111) becomes an
-        // all-reduce(max) of the two CFL maxima: the min of the quotients is the quotient of the max.
         if (int rc = comm_begin(s)) return rc;
-        ARMON_NCCL(ncclAllReduce(&s->ts->acc[0][0], &s->ts->acc[0][0], 2, ncclUint64, ncclMax, s->ctx->comm,
+        ARMON_NCCL(ncclAllReduce(&s->ts->acc[slot][0], &s->ts->acc[slot][0], 2, ncclUint64, ncclMax, s->ctx->comm,
                                  s->ctx->comm_stream));
-        if (int rc = comm_end(s, true)) return rc;
+        ARMON_CUDA(cudaEventRecord(s->ev_dt[slot], s->ctx->comm_stream));
+        if (wait) ARMON_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->ev_dt[slot], 0));
     }
     return ARMON_OK;
 }
 
-int launch_cycle_step(armon_solver *s, bool first, bool acc_is_xy)
+int wait_allreduce(armon_solver *s, int slot)
+{
+    if (s->ctx->comm && s->ctx->nranks > 1) ARMON_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->ev_dt[slot], 0));
+    return ARMON_OK;
+}
+
+int launch_cycle_step(armon_solver *s, bool first, long long k, int read_slot, bool acc_is_xy)
 {
     CycleStepArgs a;
     a.first = first ? 1 : 0;
+    a.k = k;
+    a.read_slot = read_slot;
     a.acc_is_xy = acc_is_xy ? 1 : 0;
     a.dx = s->d.domain_size[0] / (double)s->d.global_nx;
     a.dy = s->d.domain_size[1] / (double)s->d.global_ny;
@@ -558,24 +571,33 @@ int launch_init_dt(armon_solver *s)
 int enqueue_cycle(armon_solver *s)
 {
     if (!s->started) {
-        // cycle 0: EOS_init + first time step (src/solver.jl:291-297)
+        // cycle 0: EOS_init + first time step (src/solver.jl:291-297); its maxima go to slot 1 ("cycle -1")
         if (int rc = launch_init_dt(s)) return rc;
-        if (int rc = allreduce_acc(s)) return rc;
-        if (int rc = launch_cycle_step(s, true, true)) return rc;
+        if (int rc = allreduce_acc(s, 1, true)) return rc;
+        if (int rc = launch_cycle_step(s, true, -1, 1, true)) return rc;
         s->started = true;
     }
     int axes[3], next_axes[3];
     double factors[3], next_factors[3];
-    const int n = split_axes(s->d.splitting, s->host_cycle, axes, factors);
-    split_axes(s->d.splitting, s->host_cycle + 1, next_axes, next_factors);
-    for (int k = 0; k < n; k++) {
-        const bool last = k == n - 1;
-        const int next_axis = last ? next_axes[0] : axes[k + 1];
-        if (int rc = launch_sweep(s, axes[k], factors[k], last, next_axis)) return rc;
+    const long long k = s->host_cycle;
+    const int n = split_axes(s->d.splitting, k, axes, factors);
+    split_axes(s->d.splitting, k + 1, next_axes, next_factors);
+    for (int i = 0; i < n; i++) {
+        const bool last = i == n - 1;
+        const int next_axis = last ? next_axes[0] : axes[i + 1];
+        if (int rc = launch_sweep(s, axes[i], factors[i], last, next_axis)) return rc;
     }
-    if (int rc = allreduce_acc(s)) return rc;
-    // the last sweep ran along axes[n-1]: acc[0] = (march axis, transverse axis)
-    if (int rc = launch_cycle_step(s, false, axes[n - 1] == ARMON_AXIS_X)) return rc;
+    // the last sweep ran along axes[n-1]: slot k & 1 = (march axis, transverse axis).  Its all-reduce overlaps cycle k+1.
+    if (int rc = allreduce_acc(s, (int)(k & 1), false)) return rc;
+    s->last_axis_is_x[k & 1] = axes[n - 1] == ARMON_AXIS_X;
+    // next_cycle! of cycle k; the time step D_k it installs comes from the maxima of cycle k-1 (none after cycle 0)
+    if (k >= 1) {
+        const int rs = (int)((k - 1) & 1);
+        if (int rc = wait_allreduce(s, rs)) return rc;
+        if (int rc = launch_cycle_step(s, false, k, rs, s->last_axis_is_x[rs])) return rc;
+    } else {
+        if (int rc = launch_cycle_step(s, false, k, -1, true)) return rc;
+    }
     s->host_cycle++;
     return ARMON_OK;
 }
@@ -738,6 +760,8 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_state, cudaEventDisableTiming));
     ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
     ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_edge, cudaEventDisableTiming));
+    ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_dt[0], cudaEventDisableTiming));
+    ARMON_CUDA(cudaEventCreateWithFlags(&s->ev_dt[1], cudaEventDisableTiming));
     ARMON_CUDA(cudaStreamCreateWithFlags(&s->edge_stream, cudaStreamNonBlocking));
     k_ts_reset<<<1, 1, 0, ctx->stream>>>(s->ts, desc->cst_dt, desc->Dt);
     ARMON_LAUNCH_CHECK(ctx);
@@ -758,6 +782,7 @@ int armon_solver_destroy(armon_solver *s)
     if (s->ev_state) cudaEventDestroy(s->ev_state);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
     if (s->ev_edge) cudaEventDestroy(s->ev_edge);
+    for (int k = 0; k < 2; k++) if (s->ev_dt[k]) cudaEventDestroy(s->ev_dt[k]);
     if (s->edge_stream) cudaStreamDestroy(s->edge_stream);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     delete s;
