@@ -76,3 +76,37 @@ def test_axis_splitting_and_steps_ranges():
     assert armon.block_domain_range(p.N, sx.cell_update) == (1 - 2, 20 + 2, 1, 10)
     assert armon.block_domain_range(p.N, sx.advection) == (1, 21, 1, 10)
     assert armon.block_domain_range(p.N, p.steps_ranges[1].fluxes) == (1, 20, 1 - 2, 10 + 3)
+
+
+def test_host_time_step_state_machine_matches_oracle():
+    """GlobalTimeStep (the per-step path's mirror of update_dt! / next_cycle!, src/solver_state.jl:102-166) driven with
+    the oracle's local time steps reproduces the oracle's own dt sequence bit for bit, including the one-cycle lag and
+    the 5 % growth cap."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import reference_params
+    from oracle import OracleSolver
+    from armon_jl_b200 import GlobalTimeStep
+
+    params = reference_params("Sod_circ", N=(48, 40), maxcycle=25)
+    a = OracleSolver(params, "strict", nthreads=1)       # runs its own state machine
+    b = OracleSolver(params, "strict", nthreads=1)       # stepped by hand with the Python state machine
+    gdt = GlobalTimeStep()
+    gdt.reset(params)
+    for cycle in range(25):
+        a.solver_cycle()
+        if cycle == 0:
+            for axis in (0,):
+                b.step_EOS(axis)                              # EOS_init (src/solver.jl:291-295)
+        gdt.update_dt(params, b.local_time_step())            # next_time_step (src/reductions.jl:164-199)
+        dt = gdt.current_dt
+        for axis in (0, 1):                                   # Sequential splitting
+            b.sweep(axis, dt)
+        gdt.next_cycle(params)
+        assert gdt.cycle == a.state.cycle and gdt.time == a.state.time and gdt.current_dt == a.state.current_dt, cycle
+    assert np_equal(a.real("rho"), b.real("rho")) and np_equal(a.real("E"), b.real("E"))
+
+
+def np_equal(x, y):
+    import numpy as np
+    return bool(np.array_equal(x, y))
