@@ -235,32 +235,116 @@ end
 
 # ------------------------------------------------------------------------------------------------------------
 # Seam 2b: per-step overloads (debug / `compare=true` checkpoints, src/io.jl:185-227): one ccall per
-# `@generic_kernel`.  Shown for two kernels; the remaining ones (armon_bizarrium_EOS, armon_boundary_conditions,
-# armon_acoustic, armon_cell_update, armon_advection_first_order/_second_order, armon_euler_projection,
-# armon_dtCFL, armon_conservation_vars, armon_init_test) follow the same pattern, argument for argument.
+# `@generic_kernel`, same per-block wrapper signatures as the reference (src/kernels.jl:151-230,
+# src/riemann_schemes.jl:46-123, src/projection_schemes.jl:44-145, src/halo_exchange.jl:32-36, src/reductions.jl:65-110,
+# 271-298).  They are what `solver_cycle` falls back to when `params.compare` is set (see above).
 # ------------------------------------------------------------------------------------------------------------
-c_domain(blk, range) = CDomain(Armon.real_corners(blk.size, range)...)   # block_domain_range, src/blocking/blocking.jl:71-85
-c_dims(blk) = CDims(Armon.real_block_size(blk.size)..., Armon.ghosts(blk.size))
+const B200Params = ArmonParameters{<:Any, <:B200Device}
+const PF = Ptr{Float64}
 
-function Armon.update_EOS!(params::ArmonParameters{<:Any, <:B200Device}, state::SolverState, blk::LocalTaskBlock,
-                           ::Armon.TestCase)
+# block_domain_range(bsize, steps_range) -> inclusive rectangle in 1-based real-cell coordinates (armon_domain)
+function c_domain(blk::LocalTaskBlock, range)
+    (nx, ny) = Armon.real_block_size(blk.size)
+    ((blx, bly), (trx, try_)) = (Tuple(range[1]), Tuple(range[2]))     # corner offsets of a StepsRanges entry
+    CDomain(1 + blx, nx + trx, 1 + bly, ny + try_)
+end
+c_dims(blk::LocalTaskBlock) = CDims(Armon.real_block_size(blk.size)..., Armon.ghosts(blk.size))
+c_axis(state::SolverState) = Cint(Int(state.axis) - 1)
+swept_velocity(state::SolverState, d) = state.axis == Axis.X ? d.u : d.v
+
+function Armon.update_EOS!(params::B200Params, state::SolverState, blk::LocalTaskBlock, tc::Armon.TestCase)
     d = Armon.block_device_data(blk)
-    @b200call(:armon_perfect_gas_EOS,
-              (Ptr{Cvoid}, CDims, CDomain, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+    @b200call(:armon_perfect_gas_EOS, (Ptr{Cvoid}, CDims, CDomain, Float64, PF, PF, PF, PF, PF, PF, PF),
               params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.EOS),
-              Armon.specific_heat_ratio(state.test_case), d.ρ, d.E, d.u, d.v, d.p, d.c, d.g)
+              Armon.specific_heat_ratio(tc), d.ρ, d.E, d.u, d.v, d.p, d.c, d.g)
 end
 
-function Armon.numerical_fluxes!(params::ArmonParameters{<:Any, <:B200Device}, state::SolverState,
-                                 blk::LocalTaskBlock, ::Armon.RiemannGAD)
+function Armon.update_EOS!(params::B200Params, state::SolverState, blk::LocalTaskBlock, ::Armon.Bizarrium)
     d = Armon.block_device_data(blk)
-    ua = state.axis == Axis.X ? d.u : d.v
-    @b200call(:armon_acoustic_GAD,
-              (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, Float64, Cint, Ptr{Float64}, Ptr{Float64},
-               Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.fluxes), Int(state.axis) - 1,
-              state.dt, state.dx, limiter_code(state.riemann_limiter), d.uˢ, d.pˢ, d.ρ, ua, d.p, d.c)
+    @b200call(:armon_bizarrium_EOS, (Ptr{Cvoid}, CDims, CDomain, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.EOS), d.ρ, d.u, d.v, d.E, d.p, d.c, d.g)
+end
+
+function Armon.boundary_conditions!(params::B200Params, state::SolverState, blk::LocalTaskBlock, side::Side.T)
+    d = Armon.block_device_data(blk)
+    (u_factor, v_factor) = Armon.boundary_condition(state.test_case, side)
+    @b200call(:armon_boundary_conditions, (Ptr{Cvoid}, CDims, Cint, Float64, Float64, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), Cint(Int(side) - 1), u_factor, v_factor, d.ρ, d.u, d.v, d.p, d.c, d.g, d.E)
+end
+
+function Armon.numerical_fluxes!(params::B200Params, state::SolverState, blk::LocalTaskBlock, ::Armon.RiemannGodunov)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_acoustic, (Ptr{Cvoid}, CDims, CDomain, Cint, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.fluxes), c_axis(state),
+              d.uˢ, d.pˢ, d.ρ, swept_velocity(state, d), d.p, d.c)
+end
+
+function Armon.numerical_fluxes!(params::B200Params, state::SolverState, blk::LocalTaskBlock, ::Armon.RiemannGAD)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_acoustic_GAD, (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, Float64, Cint, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.fluxes), c_axis(state),
+              state.dt, state.dx, limiter_code(state.riemann_limiter), d.uˢ, d.pˢ, d.ρ, swept_velocity(state, d), d.p, d.c)
+end
+
+function Armon.cell_update!(params::B200Params, state::SolverState, blk::LocalTaskBlock)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_cell_update, (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, Float64, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.cell_update), c_axis(state),
+              state.dx, state.dt, d.uˢ, d.pˢ, d.ρ, swept_velocity(state, d), d.E)
+end
+
+function Armon.advection_fluxes!(params::B200Params, state::SolverState, blk::LocalTaskBlock, ::Armon.EulerProjection)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_advection_first_order, (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.advection), c_axis(state), state.dt,
+              d.uˢ, d.ρ, d.u, d.v, d.E, d.work_1, d.work_2, d.work_3, d.work_4)
+end
+
+function Armon.advection_fluxes!(params::B200Params, state::SolverState, blk::LocalTaskBlock, ::Armon.Euler2ndProjection)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_advection_second_order,
+              (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, Float64, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.advection), c_axis(state), state.dx, state.dt,
+              d.uˢ, d.ρ, d.u, d.v, d.E, d.work_1, d.work_2, d.work_3, d.work_4)
+end
+
+function Armon.euler_projection!(params::B200Params, state::SolverState, blk::LocalTaskBlock)
+    d = Armon.block_device_data(blk)
+    @b200call(:armon_euler_projection, (Ptr{Cvoid}, CDims, CDomain, Cint, Float64, Float64, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), c_domain(blk, state.steps_ranges.projection), c_axis(state), state.dx, state.dt,
+              d.uˢ, d.ρ, d.u, d.v, d.E, d.work_1, d.work_2, d.work_3, d.work_4)
+end
+
+# dtCFL_kernel(params, state, blk, ΔX), src/reductions.jl:65-88: returns the host value like `mapreduce`
+function Armon.dtCFL_kernel(params::B200Params, ::SolverState, blk::LocalTaskBlock, ΔX)
+    d = Armon.block_device_data(blk)
+    res = Ref{Float64}(Inf)
+    @b200call(:armon_dtCFL, (Ptr{Cvoid}, CDims, PF, PF, PF, Float64, Float64, Ptr{Float64}),
+              params.device.ctx, c_dims(blk), d.u, d.v, d.c, ΔX[1], ΔX[2], res)
+    return res[]
+end
+
+# conservation_vars(params, blk), src/reductions.jl:271-298 -> (mass, energy) of the block
+function Armon.conservation_vars(params::B200Params, blk::LocalTaskBlock)
+    d = Armon.block_device_data(blk)
+    ds = prod(params.domain_size ./ params.global_grid)
+    mass, energy = Ref{Float64}(0), Ref{Float64}(0)
+    @b200call(:armon_conservation_vars, (Ptr{Cvoid}, CDims, PF, PF, Float64, Ptr{Float64}, Ptr{Float64}),
+              params.device.ctx, c_dims(blk), d.ρ, d.E, ds, mass, energy)
+    return (mass[], energy[])
+end
+
+# init_test(params, blk), src/kernels.jl:176-214: full domain including ghosts (per-step path; the fused path uses
+# armon_solver_init above)
+function Armon.init_test(params::B200Params, blk::LocalTaskBlock)
+    d = Armon.block_device_data(blk)
+    tc = Ref(c_test_case(params))
+    ds, org = collect(Float64, params.domain_size), collect(Float64, params.origin)
+    @b200call(:armon_init_test,
+              (Ptr{Cvoid}, CDims, Int64, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{CTestCase},
+               PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF, PF),
+              params.device.ctx, c_dims(blk), params.N_origin..., params.global_grid..., ds, org, tc,
+              d.x, d.y, d.mask, d.ρ, d.E, d.u, d.v, d.p, d.c, d.g, d.uˢ, d.pˢ, d.work_1, d.work_2, d.work_3, d.work_4)
 end
 
 end # module
