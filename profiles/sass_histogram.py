@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Static instruction budget of the steady-state loop of a sweep kernel (no GPU needed).
+
+  python profiles/sass_histogram.py armon.jl_b200/build/sweep_async2_inst_fast_pg.o sweep_async2_kernelI2fdLi2ELi2ELi1ELi0ELi1E
+
+Finds the innermost-but-largest backward branch of the function (the 4-step unrolled march loop), stops at the first
+forward branch out of it (the staging flush that runs every second iteration) and prints the opcode histogram per march
+step (= per row of 32 cells and warp)."""
+import collections
+import re
+import subprocess
+import sys
+
+
+def main():
+    obj, pat = sys.argv[1], sys.argv[2]
+    out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+    lines, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            on = pat in ln
+        if on:
+            m = re.match(r"\s*/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
+            if m:
+                lines.append((int(m.group(1), 16), m.group(2).strip()))
+    back = [(a, i) for a, i in lines
+            if (t := re.search(r"BRA(?:\.U)?\s+(?:!?U?P\w+,\s*)?0x([0-9a-f]+)", i)) and int(t.group(1), 16) < a]
+    end, ins = back[-1]
+    start = int(re.search(r"0x([0-9a-f]+)", ins).group(1), 16)
+    body = [(a, i) for a, i in lines if start <= a < end]
+    stop = [a for a, i in body if re.search(r"@P0 BRA 0x", i)][0]
+    c = collections.Counter()
+    for a, i in body:
+        if a >= stop:
+            break
+        op = re.sub(r"^@!?U?P\w+\s+", "", i).split()[0]
+        op = op if op.startswith(("IMAD.MOV", "MUFU")) else op.split(".")[0]
+        c[op] += 1
+    tot = sum(c.values())
+    fp64 = sum(v for k, v in c.items() if k in ("DFMA", "DMUL", "DADD", "DSETP"))
+    print(f"loop 0x{start:x}..0x{stop:x}: {tot} instructions per 4 steps = {tot / 4:.1f} per step, FP64 {fp64 / 4:.1f} per step")
+    for k, v in c.most_common():
+        print(f"  {k:14s} {v / 4:6.2f}")
+
+
+if __name__ == "__main__":
+    main()
