@@ -110,3 +110,9 @@ def test_host_time_step_state_machine_matches_oracle():
 def np_equal(x, y):
     import numpy as np
     return bool(np.array_equal(x, y))
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(armon.SolverException) as e:
+        backend.load_library(str(tmp_path / "libarmon_b200.so"))
+    assert e.value.category == "cpp" and "no CPU fallback" in str(e.value)
