@@ -16,6 +16,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "armon_b200.h")
 
 ARMON_OK, ARMON_ERR_INVALID, ARMON_ERR_CUDA, ARMON_ERR_NCCL, ARMON_ERR_TIME, ARMON_ERR_NO_DEVICE, ARMON_ERR_RANGE = range(7)
 MATH_MODES = {"strict": 0, "fast": 1, "ieee": 2}
+KERNEL_VARIANTS = {"auto": 0, "single": 1, "async": 4, "async2": 5}      # ARMON_KERNEL_*
+CUDA_GRAPH_MODES = {"auto": 0, "on": 1, "off": 2}
 
 PD = C.POINTER(C.c_double)
 
@@ -46,12 +48,19 @@ class armon_solver_desc(C.Structure):
                 ("cst_dt", C.c_int32), ("Dt", C.c_double),
                 ("neighbours", C.c_int32 * 4),
                 ("math_mode", C.c_int32), ("march_segment", C.c_int32), ("kernel_variant", C.c_int32),
+                ("cuda_graph", C.c_int32),
                 ("tc", armon_test_case)]
 
 
 class armon_time_state(C.Structure):
     _fields_ = [("cycle", C.c_int64), ("time", C.c_double), ("current_dt", C.c_double),
-                ("next_cycle_dt", C.c_double), ("error", C.c_int32), ("done", C.c_int32)]
+                ("next_cycle_dt", C.c_double), ("error", C.c_int32), ("done", C.c_int32),
+                ("error_cycle", C.c_int64)]
+
+
+class armon_cycle_diag(C.Structure):
+    _fields_ = [("cycle", C.c_int64), ("time", C.c_double), ("dt", C.c_double), ("mass", C.c_double),
+                ("energy", C.c_double)]
 
 
 _VP = C.c_void_p
@@ -100,6 +109,19 @@ SIGNATURES = {
     "armon_solver_sweep_launches": [_VP, C.POINTER(C.c_uint64)],
     "armon_solver_profile": [_VP, C.c_int],
     "armon_solver_sweep_time_ms": [_VP, PD, C.POINTER(C.c_uint64)],
+    "armon_solver_diagnostics": [_VP, C.c_int32],
+    "armon_solver_read_diagnostics": [_VP, C.POINTER(armon_cycle_diag), C.c_int64, C.POINTER(C.c_int64)],
+    "armon_group_create": [_VP, C.c_int32, C.c_int32, C.POINTER(_VP), C.POINTER(_VP)],
+    "armon_group_destroy": [_VP],
+    "armon_group_init": [_VP],
+    "armon_group_reset": [_VP],
+    "armon_group_run": [_VP, C.c_int64],
+    "armon_group_time_loop": [_VP],
+    "armon_group_state": [_VP, C.POINTER(armon_time_state)],
+    "armon_group_finalize": [_VP],
+    "armon_group_elapsed_ms": [_VP, C.POINTER(C.c_float)],
+    "armon_group_diagnostics": [_VP, C.c_int32],
+    "armon_group_read_diagnostics": [_VP, C.POINTER(armon_cycle_diag), C.c_int64, C.POINTER(C.c_int64)],
     "armon_selftest_math": [_VP, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64 * 5)],
     "armon_comm_unique_id": [C.c_char * 128],
     "armon_ctx_comm_init": [_VP, C.c_char * 128, C.c_int, C.c_int],
@@ -184,6 +206,10 @@ def _free_array(handle, ptr):
 
 def _destroy_solver(handle, solver):
     handle.lib.armon_solver_destroy(solver)   # `handle` is only kept alive until here
+
+
+def _destroy_group(handle, group):
+    handle.lib.armon_group_destroy(group)
 
 
 class B200Device:

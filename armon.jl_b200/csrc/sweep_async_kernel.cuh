@@ -75,7 +75,7 @@ __device__ __forceinline__ void chunk_end(const SweepArgs &A, SweepThread &T, Ch
         if (T.valid) {
             const unsigned e = atomicAdd(A.fix_count, 1u);
             if (e < A.fix_cap) A.fix_list[e] = ((unsigned long long)mb << 32) | (unsigned long long)(unsigned)w;
-            else A.ts->error = ARMON_ERR_RANGE;
+            else A.ts->range_error = 1;   // reaches every rank through the error channel of the dt all-reduce
         }
     }
     if (C.taint > 0) {

@@ -1,13 +1,18 @@
-// sweep_dispatch.h -- table of the fused sweep kernel instantiations (one translation unit per
+// sweep_dispatch.h -- tables of the fused sweep kernel instantiations (one translation unit per kernel family x
 // arithmetic mode x EOS so that they compile in parallel).
+//
+// Families on the product path:
+//   sweep_kernel        (register prefetch)  : every math mode; the fallback for odd input pitches and math_mode ieee
+//   sweep_async_kernel  (cp.async staging)   : math_mode strict (bit-exact), + sweep_fixup_kernel
+//   sweep_async2_kernel (cp.async + skew)    : math_mode fast
 #pragma once
 #include "sweep_kernel.cuh"
-#include "sweep_ws_kernel.cuh"
-#include "sweep_tma_kernel.cuh"
+#include "sweep_fixup_kernel.cuh"
 #include "sweep_async_kernel.cuh"
 #include "sweep_async2_kernel.cuh"
 
 typedef void (*sweep_fn_t)(const SweepArgs);
+typedef void (*sweep_fixup_fn_t)(const SweepArgs, const FixupArgs);
 
 // rl: 0 = Godunov (acoustic!), 1 + limiter code = GAD with that limiter; proj: ARMON_PROJ_*
 sweep_fn_t sweep_table_ieee_pg(int rl, int proj);
@@ -30,33 +35,14 @@ sweep_fn_t sweep_table_fast_biz(int rl, int proj);
         return table[rl][proj];                                                             \
     }
 
-// Warp-specialised kernels (sweep_ws_kernel.cuh) and their IEEE fix-up kernels.
-typedef void (*sweep_ws_fn_t)(const SweepArgs, const FixupArgs);
-
-sweep_ws_fn_t sweep_ws_table_strict_pg(int rl, int proj);
-sweep_ws_fn_t sweep_ws_table_strict_biz(int rl, int proj);
-sweep_ws_fn_t sweep_ws_table_fast_pg(int rl, int proj);
-sweep_ws_fn_t sweep_ws_table_fast_biz(int rl, int proj);
-sweep_ws_fn_t sweep_fixup_table_pg(int rl, int proj);
-sweep_ws_fn_t sweep_fixup_table_biz(int rl, int proj);
-
-#define ARMON_DEFINE_WS_TABLE(NAME, R, DIV, EOS)                                             \
-    sweep_ws_fn_t NAME(int rl, int proj)                                                    \
-    {                                                                                       \
-        static const sweep_ws_fn_t table[4][2] = {                                          \
-            {sweep_ws_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_ws_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_ws_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_ws_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_ws_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
-        };                                                                                  \
-        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
-        return table[rl][proj];                                                             \
-    }
+// IEEE fix-up kernels of the strict cp.async sweep
+sweep_fixup_fn_t sweep_fixup_table_pg(int rl, int proj);
+sweep_fixup_fn_t sweep_fixup_table_biz(int rl, int proj);
 
 #define ARMON_DEFINE_FIXUP_TABLE(NAME, EOS)                                                  \
-    sweep_ws_fn_t NAME(int rl, int proj)                                                    \
+    sweep_fixup_fn_t NAME(int rl, int proj)                                                 \
     {                                                                                       \
-        static const sweep_ws_fn_t table[4][2] = {                                          \
+        static const sweep_fixup_fn_t table[4][2] = {                                       \
             {sweep_fixup_kernel<sd, 0, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_fixup_kernel<sd, 1, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
             {sweep_fixup_kernel<sd, 2, ARMON_PROJ_EULER, EOS>, sweep_fixup_kernel<sd, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
@@ -66,30 +52,9 @@ sweep_ws_fn_t sweep_fixup_table_biz(int rl, int proj);
         return table[rl][proj];                                                             \
     }
 
-// TMA-staged marching kernels (sweep_tma_kernel.cuh); same signature as the register-prefetch kernels.
-sweep_fn_t sweep_tma_table_strict_pg(int rl, int proj);
-sweep_fn_t sweep_tma_table_strict_biz(int rl, int proj);
-sweep_fn_t sweep_tma_table_fast_pg(int rl, int proj);
-sweep_fn_t sweep_tma_table_fast_biz(int rl, int proj);
-
-#define ARMON_DEFINE_TMA_TABLE(NAME, R, DIV, EOS)                                            \
-    sweep_fn_t NAME(int rl, int proj)                                                       \
-    {                                                                                       \
-        static const sweep_fn_t table[4][2] = {                                             \
-            {sweep_tma_kernel<R, DIV, 0, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 0, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_tma_kernel<R, DIV, 1, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 1, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_tma_kernel<R, DIV, 2, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 2, ARMON_PROJ_EULER_2ND, EOS>}, \
-            {sweep_tma_kernel<R, DIV, 3, ARMON_PROJ_EULER, EOS>, sweep_tma_kernel<R, DIV, 3, ARMON_PROJ_EULER_2ND, EOS>}, \
-        };                                                                                  \
-        if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
-        return table[rl][proj];                                                             \
-    }
-
 // cp.async-staged marching kernels (sweep_async_kernel.cuh); tr = 1: transposed output.
 sweep_fn_t sweep_async_table_strict_pg(int rl, int proj, int tr);
 sweep_fn_t sweep_async_table_strict_biz(int rl, int proj, int tr);
-sweep_fn_t sweep_async_table_fast_pg(int rl, int proj, int tr);
-sweep_fn_t sweep_async_table_fast_biz(int rl, int proj, int tr);
 
 #define ARMON_ASYNC_ROW(R, DIV, RLV, EOS)                                                    \
     {{sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
@@ -107,8 +72,6 @@ sweep_fn_t sweep_async_table_fast_biz(int rl, int proj, int tr);
     }
 
 // Software-pipelined cp.async-staged marching kernels (sweep_async2_kernel.cuh); tr = 1: transposed output.
-sweep_fn_t sweep_async2_table_strict_pg(int rl, int proj, int tr);
-sweep_fn_t sweep_async2_table_strict_biz(int rl, int proj, int tr);
 sweep_fn_t sweep_async2_table_fast_pg(int rl, int proj, int tr);
 sweep_fn_t sweep_async2_table_fast_biz(int rl, int proj, int tr);
 

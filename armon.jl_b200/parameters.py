@@ -217,18 +217,25 @@ class ArmonParameters:
 
     # -- init_backend(params, ::B200Device; options...), src/parameters.jl:758-778 ----------------
     def _init_backend(self, math_mode="strict", march_segment=0, fused=True, device_id=None, bind_pcg=True,
-                      kernel_variant="auto", **options):
+                      kernel_variant="auto", cuda_graph="auto", block_grid=(1, 1), **options):
         """Backend-specific options (like `armon_cpp_lib_src`/`use_md_iter` for Kokkos, ext/ArmonKokkos.jl:83-89).
 
-        math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle (branch-free
-                      correctly rounded division, operands must stay in [2^-500, 2^500] or be 0, else :cpp error);
-                      "ieee": the same with nvcc's full IEEE division (every operand, slower);
+        math_mode     "strict": IEEE order of the reference source, bit-exact against the oracle (branch-free correctly
+                      rounded division; column chunks whose operands leave its proven range -- divisors in
+                      [2^-120, 2^120], dividends 0 or in [2^-900, 2^900] -- are recomputed with the full IEEE division);
+                      "ieee": nvcc's full IEEE division everywhere (slower);
                       "fast": FMA contraction + reciprocal division (the reference's own @fastmath latitude).
         march_segment cells per marching segment along the swept axis (0 = auto).
         fused         True: one marching kernel per sweep (`solver_cycle` overload);
                       False: one kernel per reference kernel (the per-step overloads / `compare` path).
         device_id     CUDA ordinal; default LOCAL_RANK (one process per GPU).
         bind_pcg      keep p, c, g arrays so that the stale `p` the reference saves can be produced.
+        kernel_variant "auto" | "single" | "async" | "async2" (include/armon_b200.h, ARMON_KERNEL_*).
+        cuda_graph    "auto" (grids of <= 512x512 cells on one rank) | "on" | "off": replay captured cycle pairs.
+        block_grid    (bx, by) blocks per GPU: the sub-domain of this process is cut like `init_indexing` cuts the
+                      global domain (N // B, remainder on the last block) into LocalTaskBlocks that exchange their
+                      ghost rows on the device (the BlockGrid of src/blocking/block_grid.jl:46-183 with
+                      `block_size` = sub-domain / B); one process only for now.
         """
         if math_mode not in ("strict", "fast", "ieee"):
             solver_error("config", f"unknown math_mode '{math_mode}'")
@@ -236,12 +243,40 @@ class ArmonParameters:
         self.march_segment = int(march_segment)
         self.fused = bool(fused)
         self.bind_pcg = bool(bind_pcg)
-        if kernel_variant not in ("auto", "single", "ws", "tma", "async", "async2"):
+        if kernel_variant not in ("auto", "single", "async", "async2"):
             solver_error("config", f"unknown kernel_variant '{kernel_variant}'")
-        self.kernel_variant = kernel_variant   # "ws": warp-specialised producer/consumer kernel; "tma": TMA-staged inputs
+        self.kernel_variant = kernel_variant
+        if cuda_graph in (True, False):
+            cuda_graph = "on" if cuda_graph else "off"
+        if cuda_graph not in ("auto", "on", "off"):
+            solver_error("config", f"unknown cuda_graph mode '{cuda_graph}'")
+        self.cuda_graph = cuda_graph
+        self.block_grid = tuple(int(b) for b in block_grid)
+        if len(self.block_grid) != 2 or min(self.block_grid) < 1:
+            solver_error("config", f"block_grid must be two positive integers, got {block_grid}")
+        if self.block_grid != (1, 1):
+            if self.use_MPI and self.proc_size > 1:
+                solver_error("config", "several blocks per GPU are supported on one process only")
+            if not self.fused:
+                solver_error("config", "the per-step path runs on one block")
+            if any(self.N[d] // self.block_grid[d] < self.nghost for d in range(2)):
+                solver_error("config", f"sub-domain {self.N} is too small to be cut into {self.block_grid} blocks of "
+                                       f"at least {self.nghost} cells along each axis")
         self.device_id = int(os.environ.get("LOCAL_RANK", 0)) if device_id is None else int(device_id)
         self.backend_options = None   # set by BlockGrid / armon(): the library context
         return options
+
+    def block_layout(self):
+        """[(bx, by, N_block, N_origin_block)] of the blocks of this process, x fastest (`block_grid`)."""
+        B = self.block_grid
+        out = []
+        for by in range(B[1]):
+            for bx in range(B[0]):
+                pos = (bx, by)
+                n = tuple(self.N[d] // B[d] + (self.N[d] % B[d] if pos[d] == B[d] - 1 else 0) for d in range(2))
+                o = tuple(self.N_origin[d] + pos[d] * (self.N[d] // B[d]) for d in range(2))
+                out.append((bx, by, n, o))
+        return out
 
     # -- helpers ---------------------------------------------------------------------------------
     def cell_size(self):

@@ -46,11 +46,10 @@ def _dom(params, corners):
 # --------------------------------------------------------------------------------------------------------
 def init_test(params, grid):
     """init_test(params, grid), src/kernels.jl:176-214"""
-    d = grid.device_data
     if params.fused:
-        check(grid.lib.armon_solver_init(grid.solver), "armon_solver_init")
-        grid._fused_dirty = False
+        grid.init_fused()
         return
+    d = grid.device_data
     tc = fill_test_case(backend.armon_test_case(), params.test)
     ds = (C.c_double * 2)(*params.domain_size)
     org = (C.c_double * 2)(*params.origin)
@@ -166,14 +165,18 @@ def next_time_step(params, state, grid):
 
 
 def conservation_vars(params, grid):
-    """conservation_vars, src/reductions.jl:202-323 -> (mass, energy), summed over ranks by the caller if needed"""
+    """conservation_vars, src/reductions.jl:202-323 -> (mass, energy): blocks of this process summed in block order,
+    then over the ranks."""
     grid.finalize()
-    d = grid.device_data
     dX = params.cell_size()
-    m, e = C.c_double(), C.c_double()
-    check(grid.lib.armon_conservation_vars(grid.device.ctx, grid.dims, d.rho.ptr, d.E.ptr, dX[0] * dX[1],
-                                           C.byref(m), C.byref(e)), "armon_conservation_vars")
-    mass, energy = m.value, e.value
+    mass = energy = 0.0
+    for blk in grid.blocks:
+        d = blk.device_data
+        m, e = C.c_double(), C.c_double()
+        check(grid.lib.armon_conservation_vars(grid.device.ctx, blk.dims, d.rho.ptr, d.E.ptr, dX[0] * dX[1],
+                                               C.byref(m), C.byref(e)), "armon_conservation_vars")
+        mass += m.value
+        energy += e.value
     if params.use_MPI and params.proc_size > 1:
         from .distributed import allreduce_sum
         mass, energy = allreduce_sum((mass, energy))
@@ -186,8 +189,7 @@ def conservation_vars(params, grid):
 def solver_cycle(params, grid):
     """solver_cycle(params, grid), src/solver.jl:288-320.  Returns True to stop (never, on this backend)."""
     if params.fused:
-        check(grid.lib.armon_solver_run(grid.solver, 1), "armon_solver_run")
-        grid._fused_dirty = True
+        grid.run(1)
         return False
     state = grid.state
     if state.global_dt.cycle == 0:
@@ -210,10 +212,20 @@ def _sync_fused_state(params, grid):
     gdt = grid.global_dt
     gdt.cycle, gdt.time, gdt.current_dt, gdt.next_cycle_dt = st.cycle, st.time, st.current_dt, st.next_cycle_dt
     if st.error == backend.ARMON_ERR_RANGE:
-        solver_error("cpp", f"cycle {st.cycle}: a division/sqrt operand left [2^-500, 2^500]; rerun with math_mode='ieee'")
+        solver_error("cpp", f"cycle {st.error_cycle}: the work list of the strict mode's IEEE fix-up overflowed; "
+                            "rerun with math_mode='ieee'")
     if st.error:
-        solver_error("time", f"Invalid time step for cycle {st.cycle}")
+        solver_error("time", f"Invalid time step for cycle {st.error_cycle}")
     return st
+
+
+def _print_cycle_line(params, cycle, dt, t, mass, energy):
+    """The `silent <= 1` line of time_loop (src/solver.jl:359-371)."""
+    if not params.is_root:
+        return
+    dM = abs(params.initial_mass - mass) / params.initial_mass * 100 if params.initial_mass else 0.0
+    dE = abs(params.initial_energy - energy) / params.initial_energy * 100 if params.initial_energy else 0.0
+    print(f"Cycle {cycle:4d}: dt = {dt:.18f}, t = {t:.18f}, |ΔM| = {dM:#8.6g}%, |ΔE| = {dE:#8.6g}%")
 
 
 def time_loop(params, grid):
@@ -221,11 +233,21 @@ def time_loop(params, grid):
     grid.reset()
     gdt = grid.global_dt
     t1 = _time.perf_counter()
-    if params.fused and params.silent > 1 and params.animation_step == 0:
-        # whole loop on the device: exact `while time < maxtime && cycle < maxcycle`
-        check(grid.lib.armon_solver_time_loop(grid.solver), "armon_solver_time_loop")
-        grid._fused_dirty = True
+    single_rank = not (params.use_MPI and params.proc_size > 1)
+    if params.fused and params.animation_step == 0 and (params.silent > 1 or single_rank):
+        # whole loop on the device: exact `while time < maxtime && cycle < maxcycle`.  The per-cycle log of
+        # `silent <= 1` is produced there too (a reduction over the state each cycle leaves, appended to a device
+        # ring): no finalize, no blocking read per cycle; the lines are printed when the loop returns.
+        verbose = params.silent <= 1
+        if verbose:
+            grid.diagnostics(max(16, min(params.maxcycle + 1, 1 << 20)))
+        grid.run_time_loop()
         _sync_fused_state(params, grid)
+        if verbose:
+            grid.cycle_log = grid.read_diagnostics()
+            for cycle, t, dt, mass, energy in grid.cycle_log:
+                _print_cycle_line(params, cycle, dt, t, mass, energy)
+            grid.diagnostics(0)
     else:
         while gdt.time < params.maxtime and gdt.cycle < params.maxcycle:
             if solver_cycle(params, grid):
@@ -236,11 +258,7 @@ def time_loop(params, grid):
                 gdt.next_cycle(params)
             if params.silent <= 1:
                 mass, energy = conservation_vars(params, grid)
-                if params.is_root:
-                    dM = abs(params.initial_mass - mass) / params.initial_mass * 100 if params.initial_mass else 0.0
-                    dE = abs(params.initial_energy - energy) / params.initial_energy * 100 if params.initial_energy else 0.0
-                    print(f"Cycle {gdt.cycle:4d}: dt = {gdt.current_dt:.18f}, t = {gdt.time:.18f}, "
-                          f"|ΔM| = {dM:#8.6g}%, |ΔE| = {dE:#8.6g}%")
+                _print_cycle_line(params, gdt.cycle, gdt.current_dt, gdt.time, mass, energy)
     params.backend_options.wait()                  # "Last fence"
     t2 = _time.perf_counter()
     solve_time = t2 - t1
@@ -265,9 +283,7 @@ def armon(params):
     final_time, dt, cycles, cells_per_sec, solve_time = time_loop(params, grid)
     device_ms = 0.0
     if params.fused and cycles > 0:
-        ms = C.c_float()
-        check(grid.lib.armon_solver_elapsed_ms(grid.solver, C.byref(ms)))
-        device_ms = ms.value
+        device_ms = grid.elapsed_ms()
     if params.check_result and params.test.is_conservative:
         mass, energy = conservation_vars(params, grid)
         dM = abs(params.initial_mass - mass)

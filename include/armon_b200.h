@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ARMON_B200_ABI_VERSION 1
+#define ARMON_B200_ABI_VERSION 2
 
 enum {
     ARMON_OK = 0,
@@ -39,9 +39,10 @@ enum {
     ARMON_ERR_NCCL = 3,      /* NCCL failure                              -> SolverException(:cpp)    */
     ARMON_ERR_TIME = 4,      /* invalid time step, src/solver_state.jl:123-124 -> SolverException(:time) */
     ARMON_ERR_NO_DEVICE = 5, /* no CUDA device: the backend has no CPU fallback */
-    ARMON_ERR_RANGE = 6      /* math_mode strict: a division/sqrt operand left the range in which the branch-free
-                                correctly-rounded routines are exact (|x| in [2^-500, 2^500] or 0); rerun with
-                                math_mode ieee                                  -> SolverException(:cpp)    */
+    ARMON_ERR_RANGE = 6      /* math_mode strict: the work list of the IEEE fix-up overflowed (more than 4 Mi column
+                                chunks of one sweep held division/sqrt operands outside the range in which the
+                                branch-free correctly rounded routines are proven: divisors in [2^-120, 2^120],
+                                dividends 0 or in [2^-900, 2^900]); rerun with math_mode ieee -> SolverException(:cpp) */
 };
 
 /* src/utils.jl:15-78 (Axis.X=1.. in Julia; 0-based here) */
@@ -58,14 +59,23 @@ enum { ARMON_SPLIT_SEQUENTIAL = 0, ARMON_SPLIT_GODUNOV = 1, ARMON_SPLIT_STRANG =
 enum { ARMON_EOS_PERFECT_GAS = 0, ARMON_EOS_BIZARRIUM = 1 };                    /* src/kernels.jl:151-161 */
 /* arithmetic mode of the fused sweep kernels */
 enum { ARMON_MATH_STRICT = 0,   /* IEEE operation order of the reference source, no FMA contraction, correctly rounded
-                                   branch-free division/sqrt: bit-exact vs the oracle; operands outside
-                                   [2^-500, 2^500] (other than 0) raise ARMON_ERR_RANGE instead of being mis-rounded */
+                                   branch-free division/sqrt: bit-exact vs the oracle; column chunks whose operands leave
+                                   the proven range (divisors [2^-120, 2^120], dividends 0 or [2^-900, 2^900]) are
+                                   recomputed with the full IEEE division by a fix-up kernel */
        ARMON_MATH_FAST = 1,     /* FMA contraction + reciprocal-based division (<= 2 ulp), like the reference's own
                                    @fastmath kernels (src/generic_kernel.jl:2-4) */
        ARMON_MATH_IEEE = 2 };   /* as STRICT but with nvcc's full IEEE division/sqrt (slow paths for every operand) */
 
+/* marching kernel of the fused sweep.  AUTO: ASYNC2 for math_mode fast, ASYNC for strict, SINGLE for ieee and
+ * whenever the input pitch is odd (16-byte staging copies need an even pitch). */
+enum { ARMON_KERNEL_AUTO = 0,
+       ARMON_KERNEL_SINGLE = 1,  /* register prefetch, no shared-memory staging */
+       ARMON_KERNEL_ASYNC = 4,   /* inputs staged through shared memory with cp.async */
+       ARMON_KERNEL_ASYNC2 = 5   /* cp.async staging + software-pipelined step */ };
+
 typedef struct armon_ctx armon_ctx;
 typedef struct armon_solver armon_solver;
+typedef struct armon_group armon_group;
 
 /* Block geometry: StaticBSize/DynamicBSize (src/blocking/blocking.jl:19-58) with one block per GPU. */
 typedef struct { int64_t nx, ny, g; } armon_dims;
@@ -100,7 +110,9 @@ typedef struct {
     int32_t neighbours[4];           /* rank of the neighbour per side, -1 = global edge (MPI.PROC_NULL), params.neighbours */
     int32_t math_mode;               /* ARMON_MATH_* */
     int32_t march_segment;           /* cells per marching segment along the swept axis (0 = auto) */
-    int32_t kernel_variant;          /* 0 = auto, 1 = register-prefetch marching kernel, 2 = warp-specialised (producer/consumer), 3 = TMA-staged inputs, 4 = cp.async-staged inputs, 5 = cp.async-staged, software-pipelined step */
+    int32_t kernel_variant;          /* ARMON_KERNEL_*: 0 = auto */
+    int32_t cuda_graph;              /* 0 = auto (grids of <= 512x512 cells on one rank), 1 = replay captured cycle
+                                        pairs with a CUDA graph, 2 = never */
     armon_test_case tc;
 } armon_solver_desc;
 
@@ -112,7 +124,15 @@ typedef struct {
     double  next_cycle_dt;
     int32_t error;                   /* ARMON_ERR_TIME when an invalid time step was met */
     int32_t done;                    /* 1 once time >= maxtime or cycle >= maxcycle (src/solver.jl:333) */
+    int64_t error_cycle;             /* cycle the reference's message would name (src/solver_state.jl:123-124) */
 } armon_time_state;
+
+/* One line of the reference's per-cycle log (src/solver.jl:359-371), produced on the device. */
+typedef struct {
+    int64_t cycle;                   /* global_dt.cycle after next_cycle! */
+    double  time, dt;                /* global_dt.time, global_dt.current_dt */
+    double  mass, energy;            /* conservation_vars of this rank's blocks (src/reductions.jl:202-298) */
+} armon_cycle_diag;
 
 /* ---------------------------------------------------------------------------------------------------
  * ABI self-description and errors (ext/ArmonKokkos.jl:72-76,119-140)
@@ -241,6 +261,39 @@ int armon_solver_profile(armon_solver *solver, int enable);
 int armon_solver_sweep_time_ms(armon_solver *solver, double *total_ms, uint64_t *count);
 /* kernel + launch statistics of the fused path */
 int armon_solver_sweep_launches(armon_solver *solver, uint64_t *count);
+
+/* Per-cycle diagnostics without a host round trip: the reference's `silent <= 1` log line (src/solver.jl:359-371:
+ * wait + conservation_vars + print after every cycle).  While enabled, every cycle enqueues a fixed-tree reduction of
+ * (sum rho, sum rho*E) * dx*dy over the real cells of the state it produced, in whatever layout the last sweep left
+ * it (no finalize, no copy), and appends {cycle, time, dt, mass, energy} to a device ring of `capacity` lines.
+ * `armon_solver_read_diagnostics` blocks, copies out the lines appended since the last read (oldest first, at most
+ * `max_lines`) and returns their number; lines of cycles enqueued past the end of the run are dropped. */
+int armon_solver_diagnostics(armon_solver *solver, int32_t capacity);     /* 0 disables */
+int armon_solver_read_diagnostics(armon_solver *solver, armon_cycle_diag *lines, int64_t max_lines, int64_t *n_lines);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Several blocks per GPU: a BlockGrid of LocalTaskBlocks (src/blocking/block_grid.jl:46-183) advanced in lock step.
+ * `blocks` are nbx*nby bound solvers created on the same context, block (bx, by) at index by*nbx + bx, each
+ * describing its own sub-domain (dims, origin_ix/iy) of the same global grid; sides that face another block of the
+ * group must have neighbours[side] == -1 in the descriptor.  The group replaces, between those blocks,
+ * `block_ghost_exchange(params, state, blk1::LocalTaskBlock, blk2::LocalTaskBlock, side)` (src/halo_exchange.jl:
+ * 107-121,172-186: the g innermost real strips of one block become the g ghost strips of the other) by one
+ * device-to-device copy per variable and side -- in the marching layout the strips are g contiguous array rows -- and
+ * shares one device-resident GlobalTimeStep: the CFL maxima of all blocks meet in the same accumulators
+ * (`next_time_step`'s loop over `all_blocks`, src/reductions.jl:91-110).  Results are bit-identical to one block
+ * covering the whole sub-domain.  A grouped solver may only be driven through its group.
+ * ------------------------------------------------------------------------------------------------- */
+int armon_group_create(armon_ctx *ctx, int32_t nbx, int32_t nby, armon_solver *const blocks[], armon_group **group);
+int armon_group_destroy(armon_group *group);          /* the solvers survive and become standalone again */
+int armon_group_init(armon_group *group);             /* armon_solver_init of every block */
+int armon_group_reset(armon_group *group);
+int armon_group_run(armon_group *group, int64_t n_cycles);
+int armon_group_time_loop(armon_group *group);
+int armon_group_state(armon_group *group, armon_time_state *out);
+int armon_group_finalize(armon_group *group);
+int armon_group_elapsed_ms(armon_group *group, float *ms);
+int armon_group_diagnostics(armon_group *group, int32_t capacity);
+int armon_group_read_diagnostics(armon_group *group, armon_cycle_diag *lines, int64_t max_lines, int64_t *n_lines);
 
 /* On-device self test: compares the branch-free division / sqrt of the strict mode with nvcc's IEEE div.rn.f64 /
  * sqrt.rn.f64 on `n_samples` pseudo-random operand pairs.  mismatch = {division, sqrt, shared-reciprocal division,

@@ -12,8 +12,7 @@ import subprocess
 import sys
 
 
-def main():
-    obj, pat = sys.argv[1], sys.argv[2]
+def histogram(obj, pat):
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
     lines, on = [], False
     for ln in out.splitlines():
@@ -38,6 +37,39 @@ def main():
         c[op] += 1
     tot = sum(c.values())
     fp64 = sum(v for k, v in c.items() if k in ("DFMA", "DMUL", "DADD", "DSETP"))
+    return start, stop, tot, fp64, c
+
+
+# kernels of the product path (GAD + minmod + euler_2nd, transposed output): key -> (object, mangled-name pattern)
+PRODUCT = {
+    "async2_fast_pg": ("sweep_async2_inst_fast_pg.o", "sweep_async2_kernelI2fdLi2ELi2ELi1ELi0ELi1E"),
+    "async2_fast_biz": ("sweep_async2_inst_fast_biz.o", "sweep_async2_kernelI2fdLi2ELi2ELi1ELi1ELi1E"),
+    "async_strict_pg": ("sweep_async_inst_strict_pg.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi0ELi1E"),
+    "async_strict_biz": ("sweep_async_inst_strict_biz.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi1ELi1E"),
+}
+
+
+def write_budget(build_dir, path):
+    """profiles/sass_budget.json: FP64 and total warp instructions per march step of the product kernels (read by
+    bench.py for the FP64 roof)."""
+    import json
+    import os
+    out = {"_doc": "static SASS count of the steady-state march loop per march step (= per cell and thread; per row of 32 "
+                   "cells and warp), python profiles/sass_histogram.py --budget armon.jl_b200/build profiles/sass_budget.json"}
+    for key, (obj, pat) in PRODUCT.items():
+        start, stop, tot, fp64, c = histogram(os.path.join(build_dir, obj), pat)
+        out[key] = {"instr_per_step": tot / 4, "fp64_per_step": fp64 / 4, "mufu_per_step": sum(v for k, v in c.items() if k.startswith("MUFU")) / 4,
+                    "kernel": pat}
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
+def main():
+    if sys.argv[1] == "--budget":
+        return write_budget(sys.argv[2], sys.argv[3])
+    obj, pat = sys.argv[1], sys.argv[2]
+    start, stop, tot, fp64, c = histogram(obj, pat)
     print(f"loop 0x{start:x}..0x{stop:x}: {tot} instructions per 4 steps = {tot / 4:.1f} per step, FP64 {fp64 / 4:.1f} per step")
     for k, v in c.most_common():
         print(f"  {k:14s} {v / 4:6.2f}")

@@ -187,13 +187,19 @@ def run_gpu(args):
     rank, world = adist.init_process_group("nccl", timeout_s=90)
     assert world == args.world
     grids = [(1, world), (world, 1)] + ([(2, world // 2)] if world >= 4 and world % 2 == 0 else [])
-    cases = [("Sod_circ", (192, 160), 12, "strict", "Sequential"), ("Sedov", (128, 128), 10, "strict", "Godunov"),
-             ("Bizarrium", (160, 96), 8, "strict", "Strang"), ("Sod_circ", (2048, 1024), 4, "fast", "Sequential")]
+    cases = [("Sod_circ", (192, 160), 12, "strict", "Sequential", 0), ("Sedov", (128, 128), 10, "strict", "Godunov", 0),
+             ("Bizarrium", (160, 96), 8, "strict", "Strang", 0), ("Sod_circ", (2048, 1024), 4, "fast", "Sequential", 0),
+             # uneven decompositions (remainder on the last rank, test/mpi.jl:551-561) and local extents of 50 cells with
+             # 16-row march segments: the last segment is 2 rows (< nghost), so the segment before it also reads ghost rows
+             # and must run with the edge launches of the overlapped sweep
+             ("Sod_circ", (107, 113), 12, "strict", "Sequential", 16),
+             ("Sod_circ", (50 * world, 50 * world), 10, "strict", "Sequential", 16),
+             ("Sod_circ", (50 * world, 50 * world), 10, "fast", "Godunov", 16)]
     if args.quick:
-        cases = cases[:1]
-    for test, global_n, cycles, math, splitting in cases:
+        cases = [cases[0], cases[5]]
+    for test, global_n, cycles, math, splitting, segment in cases:
         kw = dict(test=test, N=global_n, maxcycle=cycles, math_mode=math, axis_splitting=splitting,
-                  return_data=True, **SCHEME)
+                  march_segment=segment, return_data=True, **SCHEME)
         ref = None
         log("case", test, global_n, math, splitting)
         if rank == 0:

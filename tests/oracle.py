@@ -65,12 +65,37 @@ class orc_solver(C.Structure):
 _LIBS = {}
 
 
+def _cpu_stamp():
+    """Identity of the host CPU's instruction set: the `fast` flavour is built -march=native and must be rebuilt on
+    the machine that runs it (the built library travels with the repo snapshot)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(ln.encode()).hexdigest()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def build(force=False):
     """Compile the three oracle flavours with oracle/Makefile (gcc)."""
     targets = [os.path.join(BUILD_DIR, f"liboracle_{f}.so") for f in ("strict", "fma", "fast")]
     src_mtime = max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("armon_oracle.c", "armon_oracle.h", "Makefile"))
+    stamp_path = os.path.join(BUILD_DIR, "fast.cpustamp")
+    stamp = _cpu_stamp()
+    try:
+        with open(stamp_path) as f:
+            same_cpu = f.read().strip() == stamp
+    except Exception:
+        same_cpu = False
+    if not same_cpu and os.path.exists(targets[2]):
+        os.remove(targets[2])
     if force or not all(os.path.exists(t) and os.path.getmtime(t) >= src_mtime for t in targets):
         subprocess.run(["make", "-C", ORACLE_DIR, "CC=gcc"], check=True, capture_output=True)
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
     return targets
 
 
@@ -79,7 +104,7 @@ def load(flavour="strict"):
     if flavour in _LIBS:
         return _LIBS[flavour]
     path = os.path.join(BUILD_DIR, f"liboracle_{flavour}.so")
-    if not os.path.exists(path):
+    if not os.path.exists(path) or flavour == "fast":
         build()
     lib = C.CDLL(path)
     lib.orc_solver_create.restype = C.POINTER(orc_solver)

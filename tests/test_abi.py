@@ -35,10 +35,10 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_self_description():
     lib = armon.load_library()
-    assert lib.armon_b200_abi_version() == 1
+    assert lib.armon_b200_abi_version() == 2
     assert lib.armon_flt_size() == 8 and lib.armon_idx_size() == 8      # cf. ext/ArmonKokkos.jl:122-140
     assert C.sizeof(backend.armon_dims) == 24 and C.sizeof(backend.armon_domain) == 32
-    assert C.sizeof(backend.armon_time_state) == 40
+    assert C.sizeof(backend.armon_time_state) == 48 and C.sizeof(backend.armon_cycle_diag) == 40
 
 
 def test_no_cpu_fallback_without_a_device():

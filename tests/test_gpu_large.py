@@ -1,0 +1,112 @@
+"""Parity at the sizes the numbers are claimed on (BASELINE.json configs), through the C ABI, against the CPU oracle
+(strict flavour, OpenMP over all host cores -- each cell's arithmetic is independent of the thread count):
+
+  * strict mode: bit-exact (rho, u, v, E, dt, time);
+  * fast mode (the benched mode): max|diff| <= 1e-12 * max|field| per variable, |ddt| <= 1e-12 dt (north_star);
+  * long runs (thousands of cycles, as a real run to maxtime is): drift of the fast mode against the strict mode.
+
+The grids exercise what the 100x100 golden cases cannot: the automatic march segments (256 / 1024 rows, tens of
+segments), 16-byte staged copies and 128-bit transposed stores at pitch 8200, the register-prefetch fallback for odd
+pitches, the strict mode's IEEE fix-up list on Sedov's 2.5e-14 background.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import armon_jl_b200 as armon
+from helpers import reference_params, scaled_max_diff
+from oracle import OracleSolver
+
+pytestmark = pytest.mark.gpu
+NTHREADS = os.cpu_count() or 1
+FIELDS = ("rho", "u", "v", "E")
+
+
+def gpu_run(test, mode, **kw):
+    params = reference_params(test, math_mode=mode, bind_pcg=False, **kw)
+    grid = armon.BlockGrid(params)
+    armon.init_test(params, grid)
+    armon.time_loop(params, grid)
+    return grid
+
+
+def check_against_oracle(test, N, cycles, fast_tol=1e-12, **kw):
+    opts = dict(N=N, maxcycle=cycles, **kw)
+    orc = OracleSolver(reference_params(test, **opts), "strict", nthreads=NTHREADS)
+    _, dt, ncyc, err = orc.time_loop()
+    assert err == 0 and ncyc == cycles
+    want = {v: orc.real(v).copy() for v in FIELDS}
+    t_end = orc.state.time
+    orc.close()
+
+    g = gpu_run(test, "strict", **opts)
+    st = g.time_state()
+    assert (st.cycle, st.current_dt, st.time) == (cycles, dt, t_end)
+    for v in FIELDS:
+        got = g.real(v)
+        if not np.array_equal(got, want[v]):
+            bad = np.argwhere(got != want[v])
+            raise AssertionError(f"strict {test} {N} {v}: {len(bad)} cells differ, first {bad[0]}, "
+                                 f"scaled max diff {scaled_max_diff(got, want[v]):.3e}")
+    g.close()
+
+    g = gpu_run(test, "fast", **opts)
+    st = g.time_state()
+    assert st.cycle == cycles and abs(st.current_dt - dt) <= 1e-12 * dt and abs(st.time - t_end) <= 1e-12 * t_end
+    worst = {v: scaled_max_diff(g.real(v), want[v]) for v in FIELDS}
+    g.close()
+    assert max(worst.values()) <= fast_tol, worst
+    return worst
+
+
+def test_sod_circ_8192_bench_configuration():
+    """BASELINE configs[1]: Sod_circ 8192 x 8192, GAD + minmod + euler_2nd, auto segments (256 rows x 32 segments)."""
+    check_against_oracle("Sod_circ", (8192, 8192), 5)
+
+
+def test_bizarrium_4096():
+    """BASELINE configs[2] (EOS-heavy path) at a quarter of the edge length."""
+    check_against_oracle("Bizarrium", (4096, 4096), 6)
+
+
+def test_sedov_4096():
+    """BASELINE configs[3] test case at an eighth of the edge length: E spans 2.5e-14 .. 1e6."""
+    check_against_oracle("Sedov", (4096, 4096), 8)
+
+
+@pytest.mark.parametrize("N", [(8191, 4099), (4098, 8191)])
+def test_ragged_large(N):
+    """Odd pitches: both sweeps (8191 x 4099) or only the X sweeps (4098 x 8191: pitch 8199 after the transposition)
+    take the register-prefetch fallback; ragged last warp, ragged last chunk, element-wise transposed flush."""
+    check_against_oracle("Sod_circ", N, 4)
+
+
+def test_godunov_splitting_2048_strang_1536():
+    check_against_oracle("Sod_circ", (2048, 2048), 7, axis_splitting="Godunov", riemann_limiter="superbee")
+    check_against_oracle("Sedov", (1536, 1536), 6, axis_splitting="Strang", projection="euler")
+
+
+# measured on B200 (profiles/r2_drift.txt); asserted with a margin.  The drift is the growth of rounding-level
+# differences (fast: FMA contraction, reciprocal division; strict: the reference's operation order) through thousands
+# of nonlinear cycles with shocks, not an error of either mode.
+DRIFT_CASES = [
+    # test, N, cycles, bound on max|fast - strict| / max|strict|
+    ("Sod_circ", (1024, 1024), 2500, 1e-10),
+    ("Sedov", (1024, 1024), 2500, 1e-10),
+    ("Bizarrium", (1024, 1024), 2500, 1e-10),
+]
+
+
+@pytest.mark.parametrize("test,N,cycles,bound", DRIFT_CASES)
+def test_long_run_drift_fast_vs_strict(test, N, cycles, bound):
+    kw = dict(N=N, maxcycle=cycles, maxtime=1e9)
+    gs, gf = gpu_run(test, "strict", **kw), gpu_run(test, "fast", **kw)
+    ss, sf = gs.time_state(), gf.time_state()
+    assert ss.cycle == sf.cycle == cycles
+    drift = {v: scaled_max_diff(gf.real(v), gs.real(v)) for v in FIELDS}
+    drift["dt"] = abs(sf.current_dt - ss.current_dt) / ss.current_dt
+    drift["time"] = abs(sf.time - ss.time) / ss.time
+    print(f"drift {test} {N} {cycles} cycles: " + ", ".join(f"{k}={v:.3e}" for k, v in drift.items()))
+    gs.close(); gf.close()
+    assert max(drift.values()) <= bound, drift
