@@ -18,8 +18,11 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
+#include <cstring>
 #include <cstdlib>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace {
@@ -348,6 +351,12 @@ struct armon_solver {
     bool              use_staged = false;
     size_t            staged_smem = 0;         // dynamic shared memory per CTA of the staged kernel
     sweep_fixup_fn_t  fixup_kernel = nullptr;  // IEEE fix-up of the strict staged kernel
+    // fast-mode marching kernels (sweep_fast_kernel.cuh), [staging variant][transposed output]; `fast_stg` is the
+    // staging used for even pitches (STG_TMA or STG_CPA16), odd pitches always take STG_CPA8
+    sweep_fast_fn_t   fast_kernel[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    bool              use_fast = false;
+    int               fast_stg = STG_TMA;
+    std::map<std::tuple<const double *, long long, long long>, CUtensorMap> tmaps;   // (array, rows, pitch) -> tensor map
     bool              overlap = true;          // interior / edge split of a sweep around the halo exchange (ARMON_B200_OVERLAP=0 disables)
     unsigned         *fix_count = nullptr;     // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
@@ -528,7 +537,7 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
     }
     // as long as possible (the warm-up rows of every segment are redundant work) while keeping >= 6 waves of CTAs; the
     // staged kernels run 8 warps per SM whatever their CTA size
-    const bool staged_ok = s->use_staged && ((nw + 2 * s->d.dims.g) % 2) == 0;
+    const bool staged_ok = s->use_fast || (s->use_staged && ((nw + 2 * s->d.dims.g) % 2) == 0);
     const long long cols_per_cta = staged_ok ? ASYNC_TPB : SWEEP_TPB;
     const long long ctas_per_sm = staged_ok ? 256 / ASYNC_TPB : 2;
     const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
@@ -539,6 +548,46 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         if (ncol * ((nm + seg - 1) / seg) >= want) return seg;
     }
     return nm >= 64 ? 32 : 16;
+}
+
+// Tensor map of one input array in the marching layout: a 2-D Float64 tensor [rows][pitch], box = 4 rows x 32 columns
+// (one staging group of one warp, sweep_fast_kernel.cuh).  cuTensorMapEncodeTiled is reached through the runtime's
+// driver entry point table, so the library does not link against libcuda.  Maps are cached per (array, extent).
+typedef CUresult (*encode_tiled_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tensor_map_for(armon_solver *s, const double *arr, long long rows, long long pitch, CUtensorMap *out)
+{
+    const auto key = std::make_tuple(arr, rows, pitch);
+    const auto it = s->tmaps.find(key);
+    if (it != s->tmaps.end()) { *out = it->second; return ARMON_OK; }
+    static encode_tiled_fn_t encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        ARMON_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            armon_set_error("cuTensorMapEncodeTiled is not available in this driver");
+            return ARMON_ERR_CUDA;
+        }
+        encode = reinterpret_cast<encode_tiled_fn_t>(fn);
+    }
+    alignas(64) CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(double)};   // bytes, multiple of 16: even pitch
+    const cuuint32_t box[2] = {32u, (cuuint32_t)FK_GROUP};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(arr), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        armon_set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld array", (int)rc, rows, pitch);
+        return ARMON_ERR_CUDA;
+    }
+    s->tmaps[key] = map;
+    *out = map;
+    return ARMON_OK;
 }
 
 bool is_mirror(const armon_solver *s, int side) { return s->d.neighbours[side] < 0 && s->local_nb[side] == nullptr; }
@@ -575,6 +624,8 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     A.inv_dx = 1.0 / A.dx;
     A.dt_factor = dt_factor;
     A.gamma = tc.gamma;
+    A.gm1 = tc.gamma - 1.0;
+    A.ggm1 = tc.gamma * (tc.gamma - 1.0);
     A.ts = s->ts;
     A.acc_slot = acc_slot;
 
@@ -595,8 +646,17 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         if (int rc = comm_end(s, !overlap)) return rc;
     }
 
-    const bool staged_launch = s->use_staged && (A.pitch_in % 2) == 0;
-    const long long cols_per_cta = staged_launch ? ASYNC_TPB : SWEEP_TPB;
+    const bool fast_launch = s->use_fast;
+    const int stg = (A.pitch_in % 2) == 0 ? s->fast_stg : STG_CPA8;
+    SweepTmaMaps maps;
+    if (fast_launch && stg == STG_TMA) {
+        for (int k = 0; k < 4; k++)
+            if (int rc = tensor_map_for(s, A.in[k], A.nm + 2 * D.g, A.pitch_in, &maps.m[k])) return rc;
+    } else {
+        memset(&maps, 0, sizeof(maps));
+    }
+    const bool staged_launch = !fast_launch && s->use_staged && (A.pitch_in % 2) == 0;
+    const long long cols_per_cta = (staged_launch || fast_launch) ? ASYNC_TPB : SWEEP_TPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profile) {
         if (s->prof_used + 2 > s->prof_events.size()) {
@@ -625,7 +685,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         A.y_base = (int)y_base;
         A.y_jump = (int)y_jump;
         const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
-        if (staged_launch)
+        if (fast_launch)
+            s->fast_kernel[stg][A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
+        else if (staged_launch)
             s->staged_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->staged_smem, st>>>(A);
         else
             s->kernel<<<grid, SWEEP_TPB, 0, st>>>(A);
@@ -1104,19 +1166,49 @@ int select_kernels(armon_solver *s)
         armon_set_error("no sweep kernel for this scheme combination");
         return ARMON_ERR_INVALID;
     }
-    // kernel_variant / ARMON_B200_KERNEL: auto | single | async | async2 (include/armon_b200.h, ARMON_KERNEL_*).
-    // auto: the software-pipelined kernel for the fast mode, the unskewed cp.async kernel for the strict mode (it is
-    // register-bound either way and measures the same or better without the skew); ieee always runs `single`.
+    // kernel_variant / ARMON_B200_KERNEL: auto | single | async | async2 | tma | async2_r1 (include/armon_b200.h,
+    // ARMON_KERNEL_*).  auto: fast mode -> the explicit-arithmetic kernel with TMA staging (cp.async for odd pitches);
+    // strict mode -> the unskewed cp.async kernel (it is register-bound either way and measures the same or better
+    // without the skew) + IEEE fix-up; ieee -> `single`.
     int variant = desc->kernel_variant;
     if (const char *env = getenv("ARMON_B200_KERNEL")) {
         const std::string e(env);
         variant = e == "single" ? ARMON_KERNEL_SINGLE : e == "async" ? ARMON_KERNEL_ASYNC
-                : e == "async2" ? ARMON_KERNEL_ASYNC2 : ARMON_KERNEL_AUTO;
+                : e == "async2" ? ARMON_KERNEL_ASYNC2 : e == "tma" ? ARMON_KERNEL_TMA
+                : e == "async2_r1" ? ARMON_KERNEL_ASYNC2_R1 : ARMON_KERNEL_AUTO;
     }
     if (variant == ARMON_KERNEL_AUTO)
-        variant = desc->math_mode == ARMON_MATH_FAST ? ARMON_KERNEL_ASYNC2
+        variant = desc->math_mode == ARMON_MATH_FAST ? ARMON_KERNEL_TMA
                 : desc->math_mode == ARMON_MATH_STRICT ? ARMON_KERNEL_ASYNC : ARMON_KERNEL_SINGLE;
-    const bool want_async2 = variant == ARMON_KERNEL_ASYNC2 && desc->math_mode == ARMON_MATH_FAST;
+    const char *cv = getenv("ARMON_B200_CARVEOUT");   // percent of shared memory, -1 = driver default
+    if (desc->math_mode == ARMON_MATH_FAST && (variant == ARMON_KERNEL_TMA || variant == ARMON_KERNEL_ASYNC2)) {
+        s->fast_stg = variant == ARMON_KERNEL_TMA ? STG_TMA : STG_CPA16;
+        bool ok = true;
+        for (int stg = 0; stg < 3; stg++)
+            for (int tr = 0; tr < 2; tr++) {
+                sweep_fast_fn_t fn = nullptr;
+                if (stg == STG_TMA) fn = biz ? sweep_fast_table_tma_biz(rl, desc->projection, tr) : sweep_fast_table_tma_pg(rl, desc->projection, tr);
+                else if (stg == STG_CPA16) fn = biz ? sweep_fast_table_cpa16_biz(rl, desc->projection, tr) : sweep_fast_table_cpa16_pg(rl, desc->projection, tr);
+                else fn = biz ? sweep_fast_table_cpa8_biz(rl, desc->projection, tr) : sweep_fast_table_cpa8_pg(rl, desc->projection, tr);
+                s->fast_kernel[stg][tr] = fn;
+                ok = ok && fn != nullptr;
+                if (!fn) continue;
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(ASYNC_TPB / 32 * sizeof(FastWarpShared))));
+                // everything is staged through shared memory, L1 is of no use: all of the unified array to shared memory
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+                if (getenv("ARMON_B200_VERBOSE")) {
+                    int nb = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)fn, ASYNC_TPB,
+                                                                  ASYNC_TPB / 32 * sizeof(FastWarpShared));
+                    fprintf(stderr, "[armon_b200] fast kernel stg=%d tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n", stg,
+                            tr, nb, ASYNC_TPB / 32 * sizeof(FastWarpShared));
+                }
+            }
+        s->use_fast = ok;
+    }
+    const bool want_async2 = variant == ARMON_KERNEL_ASYNC2_R1 && desc->math_mode == ARMON_MATH_FAST;
     const bool want_async = variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT;
     if (want_async || want_async2) {
         bool ok = true;
@@ -1132,9 +1224,6 @@ int select_kernels(armon_solver *s)
             if (s->staged_kernel[tr]) {
                 ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->staged_smem));
-                // the kernel stages everything through shared memory and has no use for L1: give the whole unified
-                // array to shared memory so that 8 warps are resident per SM
-                const char *cv = getenv("ARMON_B200_CARVEOUT");   // percent of shared memory, -1 = driver default
                 ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
                                                 cudaFuncAttributePreferredSharedMemoryCarveout,
                                                 cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
@@ -1143,7 +1232,7 @@ int select_kernels(armon_solver *s)
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)s->staged_kernel[tr], ASYNC_TPB,
                                                                   s->staged_smem);
                     fprintf(stderr, "[armon_b200] staged kernel (%s) tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n",
-                            want_async2 ? "async2" : "async", tr, nb, s->staged_smem);
+                            want_async2 ? "async2_r1" : "async", tr, nb, s->staged_smem);
                 }
             }
         }
@@ -1186,7 +1275,8 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
     ARMON_CHECK_ARG(desc->math_mode == ARMON_MATH_STRICT || desc->math_mode == ARMON_MATH_FAST ||
                     desc->math_mode == ARMON_MATH_IEEE, "math mode");
     ARMON_CHECK_ARG(desc->kernel_variant == ARMON_KERNEL_AUTO || desc->kernel_variant == ARMON_KERNEL_SINGLE ||
-                    desc->kernel_variant == ARMON_KERNEL_ASYNC || desc->kernel_variant == ARMON_KERNEL_ASYNC2,
+                    desc->kernel_variant == ARMON_KERNEL_ASYNC || desc->kernel_variant == ARMON_KERNEL_ASYNC2 ||
+                    desc->kernel_variant == ARMON_KERNEL_TMA || desc->kernel_variant == ARMON_KERNEL_ASYNC2_R1,
                     "kernel variant");
     ARMON_CHECK_ARG(desc->cuda_graph >= 0 && desc->cuda_graph <= 2, "cuda_graph");
     ARMON_CHECK_ARG(!desc->cst_dt || desc->Dt != 0.0, "Dt == 0 with constant step enabled");
@@ -1272,6 +1362,7 @@ int armon_solver_bind(armon_solver *s, double *const main_vars[4], double *const
     s->cur = 0;
     s->cur_transposed = false;
     s->have_prev = false;
+    s->tmaps.clear();
     drop_graph(s->group);
     return ARMON_OK;
 }

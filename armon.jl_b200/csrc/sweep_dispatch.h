@@ -89,3 +89,29 @@ sweep_fn_t sweep_async2_table_fast_biz(int rl, int proj, int tr);
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \
     }
+
+// Fast-mode marching kernels (sweep_fast_kernel.cuh): explicit arithmetic, staged by TMA / cp.async; tr = 1: transposed
+// output.  One table per staging variant and EOS.
+#include "sweep_fast_kernel.cuh"
+typedef void (*sweep_fast_fn_t)(const SweepArgs, const SweepTmaMaps);
+sweep_fast_fn_t sweep_fast_table_tma_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_tma_biz(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_cpa16_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_cpa16_biz(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_cpa8_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_cpa8_biz(int rl, int proj, int tr);
+
+#define ARMON_FAST_ROW(STG, RLV, EOS)                                                        \
+    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
+     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1>}}
+
+#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS)                                              \
+    sweep_fast_fn_t NAME(int rl, int proj, int tr)                                          \
+    {                                                                                       \
+        static const sweep_fast_fn_t table[4][2][2] = {                                     \
+            ARMON_FAST_ROW(STG, 0, EOS), ARMON_FAST_ROW(STG, 1, EOS),                       \
+            ARMON_FAST_ROW(STG, 2, EOS), ARMON_FAST_ROW(STG, 3, EOS),                       \
+        };                                                                                  \
+        if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
+        return table[rl][proj][tr];                                                         \
+    }

