@@ -16,7 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "armon_b200.h")
 
 ARMON_OK, ARMON_ERR_INVALID, ARMON_ERR_CUDA, ARMON_ERR_NCCL, ARMON_ERR_TIME, ARMON_ERR_NO_DEVICE, ARMON_ERR_RANGE = range(7)
 MATH_MODES = {"strict": 0, "fast": 1, "ieee": 2}
-KERNEL_VARIANTS = {"auto": 0, "single": 1, "async": 4, "async2": 5, "tma": 6, "async2_r1": 7}      # ARMON_KERNEL_*
+KERNEL_VARIANTS = {"auto": 0, "single": 1, "async": 4, "async2": 5, "tma": 6}      # ARMON_KERNEL_*
 CUDA_GRAPH_MODES = {"auto": 0, "on": 1, "off": 2}
 
 PD = C.POINTER(C.c_double)

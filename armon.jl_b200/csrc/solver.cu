@@ -531,8 +531,8 @@ int comm_end(armon_solver *s, bool wait_after)
 
 int pick_segment(const armon_solver *s, long long nm, long long nw)
 {
-    if (s->d.march_segment > 0) {
-        int seg = (s->d.march_segment + SWEEP_CHUNK - 1) / SWEEP_CHUNK * SWEEP_CHUNK;
+    if (s->d.march_segment > 0) {   // a multiple of the staging chunks of every kernel (16: aligned 128-byte pieces)
+        int seg = (s->d.march_segment + 15) / 16 * 16;
         return seg;
     }
     // as long as possible (the warm-up rows of every segment are redundant work) while keeping >= 6 waves of CTAs; the
@@ -635,8 +635,11 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     // rows when the last segment is shorter than the ghost width (its cells need rows up to m1+3): it then belongs to
     // the edge launches.
     const long long nseg = (A.nm + A.seg - 1) / A.seg;
+    A.nseg = (int)nseg;
     const bool has_nb = s->d.neighbours[lo_side] >= 0 || s->d.neighbours[hi_side] >= 0;
-    const bool short_tail = A.nm - (nseg - 1) * A.seg < A.g;
+    // (the fast kernels cut their segments 4 cells earlier -- 64-byte aligned transposed stores -- so their last
+    // segment is never shorter than 5 cells)
+    const bool short_tail = !s->use_fast && A.nm - (nseg - 1) * A.seg < A.g;
     const long long n_interior = nseg - 2 - (short_tail ? 1 : 0);
     const bool overlap = has_nb && n_interior >= 1 && s->overlap;
     if (has_nb) {
@@ -1166,7 +1169,7 @@ int select_kernels(armon_solver *s)
         armon_set_error("no sweep kernel for this scheme combination");
         return ARMON_ERR_INVALID;
     }
-    // kernel_variant / ARMON_B200_KERNEL: auto | single | async | async2 | tma | async2_r1 (include/armon_b200.h,
+    // kernel_variant / ARMON_B200_KERNEL: auto | single | async | async2 | tma (include/armon_b200.h,
     // ARMON_KERNEL_*).  auto: fast mode -> the explicit-arithmetic kernel with TMA staging (cp.async for odd pitches);
     // strict mode -> the unskewed cp.async kernel (it is register-bound either way and measures the same or better
     // without the skew) + IEEE fix-up; ieee -> `single`.
@@ -1174,8 +1177,7 @@ int select_kernels(armon_solver *s)
     if (const char *env = getenv("ARMON_B200_KERNEL")) {
         const std::string e(env);
         variant = e == "single" ? ARMON_KERNEL_SINGLE : e == "async" ? ARMON_KERNEL_ASYNC
-                : e == "async2" ? ARMON_KERNEL_ASYNC2 : e == "tma" ? ARMON_KERNEL_TMA
-                : e == "async2_r1" ? ARMON_KERNEL_ASYNC2_R1 : ARMON_KERNEL_AUTO;
+                : e == "async2" ? ARMON_KERNEL_ASYNC2 : e == "tma" ? ARMON_KERNEL_TMA : ARMON_KERNEL_AUTO;
     }
     if (variant == ARMON_KERNEL_AUTO)
         variant = desc->math_mode == ARMON_MATH_FAST ? ARMON_KERNEL_TMA
@@ -1208,18 +1210,12 @@ int select_kernels(armon_solver *s)
             }
         s->use_fast = ok;
     }
-    const bool want_async2 = variant == ARMON_KERNEL_ASYNC2_R1 && desc->math_mode == ARMON_MATH_FAST;
-    const bool want_async = variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT;
-    if (want_async || want_async2) {
+    if (variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT) {
         bool ok = true;
-        s->staged_smem = ASYNC_TPB / 32 * (want_async2 ? sizeof(Async2WarpShared) : sizeof(AsyncWarpShared));
+        s->staged_smem = ASYNC_TPB / 32 * sizeof(AsyncWarpShared);
         for (int tr = 0; tr < 2; tr++) {
-            if (want_async2)
-                s->staged_kernel[tr] = biz ? sweep_async2_table_fast_biz(rl, desc->projection, tr)
-                                           : sweep_async2_table_fast_pg(rl, desc->projection, tr);
-            else
-                s->staged_kernel[tr] = biz ? sweep_async_table_strict_biz(rl, desc->projection, tr)
-                                           : sweep_async_table_strict_pg(rl, desc->projection, tr);
+            s->staged_kernel[tr] = biz ? sweep_async_table_strict_biz(rl, desc->projection, tr)
+                                       : sweep_async_table_strict_pg(rl, desc->projection, tr);
             ok = ok && s->staged_kernel[tr] != nullptr;
             if (s->staged_kernel[tr]) {
                 ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
@@ -1227,13 +1223,6 @@ int select_kernels(armon_solver *s)
                 ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
                                                 cudaFuncAttributePreferredSharedMemoryCarveout,
                                                 cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
-                if (getenv("ARMON_B200_VERBOSE")) {
-                    int nb = 0;
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void *)s->staged_kernel[tr], ASYNC_TPB,
-                                                                  s->staged_smem);
-                    fprintf(stderr, "[armon_b200] staged kernel (%s) tr=%d: %d resident CTAs/SM, %zu B shared/CTA\n",
-                            want_async2 ? "async2_r1" : "async", tr, nb, s->staged_smem);
-                }
             }
         }
         s->use_staged = ok;
@@ -1276,7 +1265,7 @@ int armon_solver_create(armon_ctx *ctx, const armon_solver_desc *desc, armon_sol
                     desc->math_mode == ARMON_MATH_IEEE, "math mode");
     ARMON_CHECK_ARG(desc->kernel_variant == ARMON_KERNEL_AUTO || desc->kernel_variant == ARMON_KERNEL_SINGLE ||
                     desc->kernel_variant == ARMON_KERNEL_ASYNC || desc->kernel_variant == ARMON_KERNEL_ASYNC2 ||
-                    desc->kernel_variant == ARMON_KERNEL_TMA || desc->kernel_variant == ARMON_KERNEL_ASYNC2_R1,
+                    desc->kernel_variant == ARMON_KERNEL_TMA,
                     "kernel variant");
     ARMON_CHECK_ARG(desc->cuda_graph >= 0 && desc->cuda_graph <= 2, "cuda_graph");
     ARMON_CHECK_ARG(!desc->cst_dt || desc->Dt != 0.0, "Dt == 0 with constant step enabled");

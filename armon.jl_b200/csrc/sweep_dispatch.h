@@ -4,12 +4,11 @@
 // Families on the product path:
 //   sweep_kernel        (register prefetch)  : every math mode; the fallback for odd input pitches and math_mode ieee
 //   sweep_async_kernel  (cp.async staging)   : math_mode strict (bit-exact), + sweep_fixup_kernel
-//   sweep_async2_kernel (cp.async + skew)    : math_mode fast
+//   sweep_fast_kernel   (TMA / cp.async)     : math_mode fast, explicit arithmetic, 4 chains per step
 #pragma once
 #include "sweep_kernel.cuh"
 #include "sweep_fixup_kernel.cuh"
 #include "sweep_async_kernel.cuh"
-#include "sweep_async2_kernel.cuh"
 
 typedef void (*sweep_fn_t)(const SweepArgs);
 typedef void (*sweep_fixup_fn_t)(const SweepArgs, const FixupArgs);
@@ -66,25 +65,6 @@ sweep_fn_t sweep_async_table_strict_biz(int rl, int proj, int tr);
         static const sweep_fn_t table[4][2][2] = {                                          \
             ARMON_ASYNC_ROW(R, DIV, 0, EOS), ARMON_ASYNC_ROW(R, DIV, 1, EOS),               \
             ARMON_ASYNC_ROW(R, DIV, 2, EOS), ARMON_ASYNC_ROW(R, DIV, 3, EOS),               \
-        };                                                                                  \
-        if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
-        return table[rl][proj][tr];                                                         \
-    }
-
-// Software-pipelined cp.async-staged marching kernels (sweep_async2_kernel.cuh); tr = 1: transposed output.
-sweep_fn_t sweep_async2_table_fast_pg(int rl, int proj, int tr);
-sweep_fn_t sweep_async2_table_fast_biz(int rl, int proj, int tr);
-
-#define ARMON_ASYNC2_ROW(R, DIV, RLV, EOS)                                                   \
-    {{sweep_async2_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_async2_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
-     {sweep_async2_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 0>, sweep_async2_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 1>}}
-
-#define ARMON_DEFINE_ASYNC2_TABLE(NAME, R, DIV, EOS)                                         \
-    sweep_fn_t NAME(int rl, int proj, int tr)                                               \
-    {                                                                                       \
-        static const sweep_fn_t table[4][2][2] = {                                          \
-            ARMON_ASYNC2_ROW(R, DIV, 0, EOS), ARMON_ASYNC2_ROW(R, DIV, 1, EOS),             \
-            ARMON_ASYNC2_ROW(R, DIV, 2, EOS), ARMON_ASYNC2_ROW(R, DIV, 3, EOS),             \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \

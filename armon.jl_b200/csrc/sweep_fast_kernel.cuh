@@ -30,6 +30,14 @@
 //    that are not stored.  Tensor maps need 16-byte aligned rows, i.e. an even pitch; for odd pitches the same kernel is
 //    instantiated with per-thread 8-byte cp.async copies (STG_CPA8), and STG_CPA16 keeps the 16-byte cp.async staging of
 //    the previous round for comparison.  All staging variants share the ring layout and the step, hence the bits.
+//
+// 4. ALIGNED TRANSPOSED STORES.  A sweep that changes axis writes its output transposed, 8 cells (64 bytes) per output
+//    row and flush.  Real cell m sits at column m + 4 of the output rows (4 ghost columns first), so chunks cut at
+//    multiples of 8 cells straddle the 64-byte units of the output (measured: a transposing copy with straddling
+//    64-byte pieces runs 18 % slower than with aligned ones, scratch microbenchmark of round 2).  The march segments
+//    of this kernel therefore start 4 cells early: segment k covers cells [k seg - 4, (k+1) seg - 4) (the first one
+//    starts with 4 masked virtual cells, the last one runs to the end of the domain), and every full chunk is one
+//    aligned 64-byte unit per output row whenever the output pitch is a multiple of 8.
 #pragma once
 
 #include <cuda.h>
@@ -46,14 +54,19 @@ constexpr int FK_NG = 4;                       // groups in the ring: rows a-3 .
 constexpr int FK_ROWS = FK_GROUP * FK_NG;      // 16 ring rows
 constexpr int FK_VS = FK_GROUP * 32;           // doubles between two variables of the same row
 constexpr int FK_GS = 4 * FK_VS;               // doubles per group
-constexpr int FK_CS = 8;                       // sound-speed ring slots (written at a, read at a-5)
+constexpr int FK_CS = 8;                       // sound-speed ring slots (written at a, read at a-7)
+#ifndef FK_K
+#define FK_K 8                                 // cells per output row and flush of the transposed stores (8 or 16)
+#endif
+constexpr int FK_PITCH = FK_K + 2;             // staging tile row pitch: rows stay 16-byte aligned, 2-way write conflicts
+static_assert(FK_K == 8 || FK_K == 16, "transposed staging chunk");
 
 struct FastWarpShared {
     double ring[FK_NG][4][FK_GROUP][32];                   // [group][variable][row in group][lane]
     double cring[FK_CS][32];
-    double stage[4 * 32 * SWEEP_STAGE_PITCH];              // transposed-store staging (flush_stage)
+    double stage[4 * 32 * FK_PITCH];                       // transposed-store staging (fast_flush)
     unsigned long long full[FK_NG];                        // mbarriers: the group's 4 boxes have landed (STG_TMA)
-    unsigned long long pad_[12];                           // keeps the next warp's ring 128-byte aligned
+    unsigned long long pad_[(128 - (4 * 32 * FK_PITCH * 8 + FK_NG * 8) % 128) / 8 % 16];   // next warp's ring 128-byte aligned
 };
 static_assert(sizeof(FastWarpShared) % 128 == 0, "per-warp shared block must keep 128-byte alignment");
 
@@ -302,10 +315,10 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
         }
         if (TR == 1) {
             double *s = J == 3 ? I.s3 : I.s0 + J;
-            s[0 * 32 * SWEEP_STAGE_PITCH] = o_r;
-            s[1 * 32 * SWEEP_STAGE_PITCH] = o_ua;
-            s[2 * 32 * SWEEP_STAGE_PITCH] = o_ut;
-            s[3 * 32 * SWEEP_STAGE_PITCH] = o_E;
+            s[0 * 32 * FK_PITCH] = o_r;
+            s[1 * 32 * FK_PITCH] = o_ua;
+            s[2 * 32 * FK_PITCH] = o_ut;
+            s[3 * 32 * FK_PITCH] = o_E;
         } else if (store) {
             const long long o = I.o_it + J * A.pitch_out;
             A.out[0][o] = o_r;
@@ -320,6 +333,45 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
     P.dl[Z0] = C_dl; P.dxl[Z0] = C_dxl; P.Lr[Z0] = C_Lr; P.Lru[Z0] = C_Lru; P.Lrt[Z0] = C_Lrt; P.LrE[Z0] = C_LrE;
 #undef ZS
+}
+
+// Transposed store of one chunk: per variable 32 columns x FK_K march cells -> FK_K contiguous doubles of 32 output
+// rows.  Fast path (full tile, even output pitch): 128-bit shared loads and global stores, 64 / FK_K output rows per
+// warp instruction.  Ragged tiles (last columns, first / last chunk of a segment, odd pitch) go element by element.
+__device__ __forceinline__ void fast_flush(const SweepArgs &A, const double *stage, long long w0, long long mb,
+                                           long long m_lo, long long m1)
+{
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    if (w0 + 32 <= A.nw && mb >= m_lo && mb + FK_K <= m1 && !(A.pitch_out & 1)) {
+        constexpr int PIECES = FK_K / 2, ROWS = 32 / PIECES;   // 16-byte pieces per row, rows per warp instruction
+        const int r0 = lane / PIECES, j = lane % PIECES;
+        const double2 *src = reinterpret_cast<const double2 *>(stage + r0 * FK_PITCH + 2 * j);
+        const long long off = (w0 + r0 + A.g) * A.pitch_out + (mb + A.g) + 2 * j;
+        const long long step = ROWS * A.pitch_out;
+#pragma unroll 1
+        for (int v = 0; v < 4; v++) {
+            double *dst = A.out[v] + off;
+#pragma unroll
+            for (int it = 0; it < 32 / ROWS; it++) {
+                const double2 val = src[(v * 32 + it * ROWS) * FK_PITCH / 2];
+                *reinterpret_cast<double2 *>(dst + it * step) = val;
+            }
+        }
+    } else {
+        const int rsub = lane / FK_K, col = lane % FK_K;
+#pragma unroll 1
+        for (int v = 0; v < 4; v++) {
+#pragma unroll 1
+            for (int it = 0; it < 32 / (32 / FK_K); it++) {
+                const int r = it * (32 / FK_K) + rsub;
+                const double val = stage[(v * 32 + r) * FK_PITCH + col];
+                const long long w = w0 + r, m = mb + col;
+                if (w < A.nw && m >= m_lo && m < m1) A.out[v][(w + A.g) * A.pitch_out + (m + A.g)] = val;
+            }
+        }
+    }
+    __syncwarp();
 }
 
 // ---- mbarrier / bulk tensor copy ----------------------------------------------------------------------------------
@@ -393,8 +445,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 
     const long long w0 = (long long)blockIdx.x * ASYNC_TPB + warp * 32;
     const long long w = w0 + lane;
-    const long long m0 = sweep_segment_index(A) * A.seg;
-    const long long m1 = (m0 + A.seg < A.nm) ? m0 + A.seg : A.nm;
+    // march segment k = [k seg - 4, (k+1) seg - 4): the first one starts with 4 virtual cells (masked), the last one
+    // runs to the end of the domain
+    const long long kseg = sweep_segment_index(A);
+    const long long m0 = kseg * A.seg - 4;
+    const long long m_lo = m0 < 0 ? 0 : m0;
+    const long long m1 = (kseg == A.nseg - 1) ? A.nm : m0 + A.seg;
 
     SweepThread T;
     T.valid = w < A.nw;
@@ -404,7 +460,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     const DeviceTimeState *ts = A.ts;
     if (ts->done) {   // see sweep_kernel: copy the state through so that the host's buffer rotation stays valid
         if (T.valid) {
-            for (long long m = m0; m < m1; m++) {
+            for (long long m = m_lo; m < m1; m++) {
                 const long long i = (m + A.g) * A.pitch_in + T.col;
                 const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
 #pragma unroll
@@ -417,11 +473,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 
     const double dt = xmul(ts->current_dt, A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
     const int len = (int)(m1 - m0);
-    const int nchunks = (len + SWEEP_CHUNK - 1) / SWEEP_CHUNK;
+    const bool first_seg = m0 < 0;
+    const int nchunks = (len + FK_K - 1) / FK_K;
     const long long a_begin = m0 - 4;
-    // Step t consumes array row a_begin + t and emits cell m0 + t - 11: 11 warm-up steps, 8 per chunk of outputs, run in
-    // groups of 4 (the last group needs 3 of its steps).
-    const int n_groups = 2 * nchunks + 3;
+    // Step t consumes array row a_begin + t and emits cell m0 + t - 11: 11 warm-up steps, FK_K per chunk of outputs, run
+    // in groups of 4 (the last group needs 3 of its steps).
+    const int n_groups = (FK_K / 4) * nchunks + 3;
 
     // benign finite state in the whole ring: the lagging stages read rows "before" the first one during warm-up, and
     // columns past the end of a row are never copied by the cp.async variants (rho = E = 1, u = v = 0, c = 1)
@@ -481,7 +538,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 #pragma unroll
             for (int r = 0; r < FK_GROUP; r++) {
                 const long long row = a_begin + (long long)FK_GROUP * G + r;
-                const bool row_ok = row <= A.nm + A.g - 1 && G < n_groups;
+                const bool row_ok = row >= -(long long)A.g && row <= A.nm + A.g - 1 && G < n_groups;
                 const long long off = ((long long)FK_GROUP * G + r) * A.pitch_in;
                 if (STG == STG_CPA16) {
                     if (L.active && row_ok) {
@@ -516,7 +573,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 
     const double *ring = &S.ring[0][0][0][lane];
     double *cring = &S.cring[0][lane];
-    double *sbase = S.stage + lane * SWEEP_STAGE_PITCH;
+    double *sbase = S.stage + lane * FK_PITCH;
     FastIter I;
     I.gb1 = ring + (FK_NG - 1) * FK_GS;   // "group -1": benign
 
@@ -549,23 +606,28 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         FK_STEP(3, 0, false)
         FK_END(it)
     }
-    // Steady state.  The cell emitted at step t is m0 + t - 11, its slot in the 8-cell transposed staging tile
-    // (t - 11) & 7: an even iteration fills slots 5, 6, 7 (the tile is complete and flushed) and 0, an odd one 1 .. 4.
+    // Steady state.  The cell emitted at step t is m0 + t - 11, its slot in the FK_K-cell transposed staging tile
+    // (t - 11) & (FK_K - 1): the first three steps of an iteration fill slots (4 it + 5 ..+ 7) & (FK_K - 1), the last one
+    // slot (4 it + 8) & (FK_K - 1); when that is 0 the tile was complete after the third step and is flushed there.
     // Steps 8 .. 10, the first three of the first iteration here, are the last warm-up steps: they run the emitting
     // code with stores and CFL maxima masked, and their tile slots are overwritten before the first flush.
 #pragma unroll 1
     for (; it < n_groups; it++) {
-        const bool odd = it & 1, live = it != 2;
+        const bool live = it != 2;
+        const int k3 = (4 * it + 8) & (FK_K - 1);
+        // cells m0 .. m0 + 3 of the first segment are virtual (m < 0): emitted at the last step of iteration 2 and the
+        // first three of iteration 3
+        const bool ok012 = T.valid && live && !(first_seg && it == 3), ok3 = T.valid && !(first_seg && it == 2);
         FK_BEGIN(it)
-        I.s0 = sbase + (odd ? 1 : 5);
-        I.s3 = sbase + (odd ? 4 : 0);
+        I.s0 = sbase + ((4 * it + 5) & (FK_K - 1));
+        I.s3 = sbase + k3;
         I.rem = len - (4 * it - 11);
         if (TR == 0) I.o_it = (m0 + (4 * it - 11) + A.g) * A.pitch_out + T.col;
-        FK_STEP(0, 1, T.valid && live)
-        FK_STEP(1, 1, T.valid && live)
-        FK_STEP(2, 1, T.valid && live)
-        if (TR == 1 && !odd && live) flush_stage(A, S.stage, w0, m0 + (4 * it - 16), m1);
-        FK_STEP(3, 1, T.valid)
+        FK_STEP(0, 1, ok012)
+        FK_STEP(1, 1, ok012)
+        FK_STEP(2, 1, ok012)
+        if (TR == 1 && k3 == 0 && live) fast_flush(A, S.stage, w0, m0 + (4 * it - 8 - FK_K), m_lo, m1);
+        FK_STEP(3, 1, ok3)
         FK_END(it)
     }
 #undef FK_STEP

@@ -43,6 +43,7 @@ struct SweepArgs {
     long long pitch_out;    // transposed output: nm + 2g, else nw + 2g
     int g;
     int seg;                // outputs per march segment, multiple of SWEEP_CHUNK
+    int nseg;               // number of march segments of the sweep, ceil(nm / seg)
     int y_base, y_jump;     // march segment handled by a CTA = y_base + blockIdx.y * y_jump (interior / edge launches)
     int transpose_out;
     int mirror_lo, mirror_hi;   // 1: global edge (ghost rows written by k_bc_fill); 0: ghost rows hold the neighbour's cells

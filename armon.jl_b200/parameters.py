@@ -230,7 +230,7 @@ class ArmonParameters:
                       False: one kernel per reference kernel (the per-step overloads / `compare` path).
         device_id     CUDA ordinal; default LOCAL_RANK (one process per GPU).
         bind_pcg      keep p, c, g arrays so that the stale `p` the reference saves can be produced.
-        kernel_variant "auto" | "single" | "async" | "async2" | "tma" | "async2_r1" (include/armon_b200.h, ARMON_KERNEL_*).
+        kernel_variant "auto" | "single" | "async" | "async2" | "tma" (include/armon_b200.h, ARMON_KERNEL_*).
         cuda_graph    "auto" (grids of <= 512x512 cells on one rank) | "on" | "off": replay captured cycle pairs.
         block_grid    (bx, by) blocks per GPU: the sub-domain of this process is cut like `init_indexing` cuts the
                       global domain (N // B, remainder on the last block) into LocalTaskBlocks that exchange their
@@ -243,7 +243,7 @@ class ArmonParameters:
         self.march_segment = int(march_segment)
         self.fused = bool(fused)
         self.bind_pcg = bool(bind_pcg)
-        if kernel_variant not in ("auto", "single", "async", "async2", "tma", "async2_r1"):
+        if kernel_variant not in ("auto", "single", "async", "async2", "tma"):
             solver_error("config", f"unknown kernel_variant '{kernel_variant}'")
         self.kernel_variant = kernel_variant
         if cuda_graph in (True, False):

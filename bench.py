@@ -295,9 +295,11 @@ class GpuJob:
         avg_s = run["sweep_ms"] / max(run["sweep_n"], 1) / 1e3
         achieved = BYTES_PER_CELL_SWEEP * self.local_cells / avg_s / 1e9
         biz = self.w["test"] == "Bizarrium"
-        kname = {"fast": "sweep_async2_kernel<fd, DIV_FAST", "strict": "sweep_async_kernel<sd, DIV_FLAGGED",
-                 "ieee": "sweep_kernel<sd, DIV_IEEE"}[self.math]
-        key = f"{os.environ.get('ARMON_B200_KERNEL') or {'fast': 'async2', 'strict': 'async', 'ieee': 'single'}[self.math]}_{self.math}_{'biz' if biz else 'pg'}"
+        variant = os.environ.get("ARMON_B200_KERNEL") or {"fast": "tma", "strict": "async", "ieee": "single"}[self.math]
+        kname = {"tma": "sweep_fast_kernel<STG_TMA", "async2": "sweep_fast_kernel<STG_CPA16",
+                 "async2_r1": "sweep_async2_kernel<fd, DIV_FAST", "async": "sweep_async_kernel<sd, DIV_FLAGGED",
+                 "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}[variant]
+        key = f"{variant}_{self.math}_{'biz' if biz else 'pg'}"
         traffic = load_profile_json("sweep_traffic.json") or {}
         t = traffic.get(key)
         budget = (load_profile_json("sass_budget.json") or {}).get(key)

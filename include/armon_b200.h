@@ -73,8 +73,7 @@ enum { ARMON_KERNEL_AUTO = 0,
        ARMON_KERNEL_SINGLE = 1,     /* register prefetch, no shared-memory staging (any math mode) */
        ARMON_KERNEL_ASYNC = 4,      /* strict: inputs staged through shared memory with cp.async + IEEE fix-up kernel */
        ARMON_KERNEL_ASYNC2 = 5,     /* fast: explicit-arithmetic software-pipelined kernel, cp.async (16-byte) staging */
-       ARMON_KERNEL_TMA = 6,        /* fast: the same kernel staged by the TMA (cp.async.bulk.tensor.2d + mbarrier) */
-       ARMON_KERNEL_ASYNC2_R1 = 7   /* fast: round-1 kernel (compiler-contracted arithmetic), kept for comparison */ };
+       ARMON_KERNEL_TMA = 6         /* fast: the same kernel staged by the TMA (cp.async.bulk.tensor.2d + mbarrier) */ };
 
 typedef struct armon_ctx armon_ctx;
 typedef struct armon_solver armon_solver;

@@ -13,6 +13,9 @@ import sys
 
 
 def histogram(obj, pat):
+    """Opcode histogram of the steady-state march loop of the kernel whose mangled name contains `pat`: the loop is the
+    backward branch with the largest span; the transposed-store flush inside it (runs once per chunk of 8 steps, found
+    by its 128-bit shared loads) is left out and reported separately."""
     out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
     lines, on = [], False
     for ln in out.splitlines():
@@ -22,19 +25,25 @@ def histogram(obj, pat):
             m = re.match(r"\s*/\*([0-9a-f]{4,5})\*/\s+(.*?);", ln)
             if m:
                 lines.append((int(m.group(1), 16), m.group(2).strip()))
-    back = [(a, i) for a, i in lines
-            if (t := re.search(r"BRA(?:\.U)?\s+(?:!?U?P\w+,\s*)?0x([0-9a-f]+)", i)) and int(t.group(1), 16) < a]
-    end, ins = back[-1]
-    start = int(re.search(r"0x([0-9a-f]+)", ins).group(1), 16)
-    body = [(a, i) for a, i in lines if start <= a < end]
-    stop = [a for a, i in body if re.search(r"@P0 BRA 0x", i)][0]
+    bra = re.compile(r"BRA(?:\.U)?(?:\.ANY)?\s+(?:!?U?P\w+,\s*)?0x([0-9a-f]+)")
+    back = [(a, int(t.group(1), 16)) for a, i in lines if (t := bra.search(i)) and int(t.group(1), 16) < a]
+    end, start = max(back, key=lambda x: x[0] - x[1])
+    body = [(a, i) for a, i in lines if start <= a <= end]
+    # flush region: from the forward branch that skips it (the last one before the first LDS.128) to that branch's target
+    lds128 = [a for a, i in body if "LDS.128" in i]
+    skip = (0, 0)
+    if lds128:
+        fwd = [(a, int(t.group(1), 16)) for a, i in body if (t := bra.search(i)) and max(lds128) < int(t.group(1), 16) <= end and a < min(lds128)]
+        if fwd:
+            skip = max(fwd, key=lambda x: x[1])   # the branch that skips the whole flush, slow path included
     c = collections.Counter()
     for a, i in body:
-        if a >= stop:
-            break
+        if skip[0] < a < skip[1]:
+            continue
         op = re.sub(r"^@!?U?P\w+\s+", "", i).split()[0]
         op = op if op.startswith(("IMAD.MOV", "MUFU")) else op.split(".")[0]
         c[op] += 1
+    stop = end
     tot = sum(c.values())
     fp64 = sum(v for k, v in c.items() if k in ("DFMA", "DMUL", "DADD", "DSETP"))
     return start, stop, tot, fp64, c
@@ -42,8 +51,10 @@ def histogram(obj, pat):
 
 # kernels of the product path (GAD + minmod + euler_2nd, transposed output): key -> (object, mangled-name pattern)
 PRODUCT = {
-    "async2_fast_pg": ("sweep_async2_inst_fast_pg.o", "sweep_async2_kernelI2fdLi2ELi2ELi1ELi0ELi1E"),
-    "async2_fast_biz": ("sweep_async2_inst_fast_biz.o", "sweep_async2_kernelI2fdLi2ELi2ELi1ELi1ELi1E"),
+    "tma_fast_pg": ("sweep_fast_inst_tma_pg.o", "sweep_fast_kernelILi0ELi2ELi1ELi0ELi1E"),
+    "tma_fast_biz": ("sweep_fast_inst_tma_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1E"),
+    "async2_fast_pg": ("sweep_fast_inst_cpa16_pg.o", "sweep_fast_kernelILi1ELi2ELi1ELi0ELi1E"),
+    "async2_fast_biz": ("sweep_fast_inst_cpa16_biz.o", "sweep_fast_kernelILi1ELi2ELi1ELi1ELi1E"),
     "async_strict_pg": ("sweep_async_inst_strict_pg.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi0ELi1E"),
     "async_strict_biz": ("sweep_async_inst_strict_biz.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi1ELi1E"),
 }

@@ -189,7 +189,7 @@ def test_cst_dt():
 
 
 # ---- 4. fast arithmetic mode: 1e-12 of field scale -------------------------------------------------------
-@pytest.mark.parametrize("variant", ["single", "async2", "tma", "async2_r1"])
+@pytest.mark.parametrize("variant", ["single", "async2", "tma"])
 @pytest.mark.parametrize("test", GOLDEN_TESTS)
 def test_fused_fast_mode_within_tolerance(test, variant, golden):
     ref = golden(test)
