@@ -1,8 +1,8 @@
 // sweep_fast_kernel.cuh -- the fast-mode marching kernel (math_mode fast: the product's default and the benched path).
 //
-// Same sweep, data layout and HBM traffic as sweep_kernel.cuh / sweep_async2_kernel.cuh (read those first: thread <->
-// column, march along the strided axis, software-pipelined step with EOS + Godunov one step ahead of the rest).  What
-// is specific to this file:
+// Same sweep, data layout and HBM traffic as sweep_kernel.cuh / sweep_async_kernel.cuh (read those first: thread <->
+// column, march along the strided axis, rolling register window, inputs staged through a per-warp shared-memory
+// ring).  What is specific to this file:
 //
 // 1. EXPLICIT ARITHMETIC.  Every floating-point operation of the step is written as an explicitly rounded intrinsic
 //    (__dadd_rn / __dmul_rn / __fma_rn): where a multiply-add is fused is decided here, not by the compiler's
@@ -25,8 +25,8 @@
 //    (cp.async.bulk.tensor.2d, SASS UTMALDG): one elected lane per warp issues, per group of 4 array rows, one copy per
 //    variable of a [4 rows x 32 columns] box into the warp's shared-memory ring and arms an mbarrier with the 4 KB it
 //    expects; the warp waits on the barrier's phase once per 4 steps.  No per-thread copy instructions, commit groups or
-//    address arithmetic in the step (sweep_async2_kernel: 2 LDGSTS + commit + wait + warp barrier + bookkeeping per
-//    step).  Out-of-range rows / columns of a ragged edge are zero-filled by the copy engine and only ever feed cells
+//    address arithmetic in the step (the cp.async staging costs 2 LDGSTS + commit + wait + warp barrier + bookkeeping
+//    per step).  Out-of-range rows / columns of a ragged edge are zero-filled by the copy engine and only ever feed cells
 //    that are not stored.  Tensor maps need 16-byte aligned rows, i.e. an even pitch; for odd pitches the same kernel is
 //    instantiated with per-thread 8-byte cp.async copies (STG_CPA8), and STG_CPA16 keeps the 16-byte cp.async staging of
 //    the previous round for comparison.  All staging variants share the ring layout and the step, hence the bits.

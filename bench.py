@@ -297,7 +297,7 @@ class GpuJob:
         biz = self.w["test"] == "Bizarrium"
         variant = os.environ.get("ARMON_B200_KERNEL") or {"fast": "tma", "strict": "async", "ieee": "single"}[self.math]
         kname = {"tma": "sweep_fast_kernel<STG_TMA", "async2": "sweep_fast_kernel<STG_CPA16",
-                 "async2_r1": "sweep_async2_kernel<fd, DIV_FAST", "async": "sweep_async_kernel<sd, DIV_FLAGGED",
+                 "async": "sweep_async_kernel<sd, DIV_FLAGGED",
                  "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}[variant]
         key = f"{variant}_{self.math}_{'biz' if biz else 'pg'}"
         traffic = load_profile_json("sweep_traffic.json") or {}

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static instruction budget of the steady-state loop of a sweep kernel (no GPU needed).
 
-  python profiles/sass_histogram.py armon.jl_b200/build/sweep_async2_inst_fast_pg.o sweep_async2_kernelI2fdLi2ELi2ELi1ELi0ELi1E
+  python profiles/sass_histogram.py armon.jl_b200/build/sweep_fast_inst_tma_pg.o sweep_fast_kernelILi0ELi2ELi1ELi0ELi1E
 
 Finds the innermost-but-largest backward branch of the function (the 4-step unrolled march loop), stops at the first
 forward branch out of it (the staging flush that runs every second iteration) and prints the opcode histogram per march
