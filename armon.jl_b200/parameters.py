@@ -241,7 +241,8 @@ class ArmonParameters:
             solver_error("config", f"unknown math_mode '{math_mode}'")
         self.math_mode = math_mode
         self.march_segment = int(march_segment)
-        self.fused = bool(fused)
+        # the step checkpoints of `compare` need every intermediate array of the reference: per-step path
+        self.fused = bool(fused) and not self.compare
         self.bind_pcg = bool(bind_pcg)
         if kernel_variant not in ("auto", "single", "async", "async2", "tma"):
             solver_error("config", f"unknown kernel_variant '{kernel_variant}'")

@@ -192,18 +192,30 @@ def solver_cycle(params, grid):
         grid.run(1)
         return False
     state = grid.state
+    from .io import step_checkpoint as _cp
+
+    def checkpoint(label):                         # @checkpoint, src/solver.jl:41-43
+        return _cp(params, state, grid, label)
+
     if state.global_dt.cycle == 0:
         state.update(params, Axis.X, 1.0)
+        if checkpoint("init_test"):
+            return True
         update_EOS(params, state, grid)            # "EOS_init"
+        if checkpoint("EOS_init"):
+            return True
     if next_time_step(params, state, grid):
+        return True
+    if checkpoint("time_step"):
         return True
     for axis, dt_factor in split_axes(state.splitting, state.global_dt.cycle):
         state.update(params, axis, dt_factor)
-        update_EOS(params, state, grid)
-        block_ghost_exchange(params, state, grid)
-        numerical_fluxes(params, state, grid)
-        cell_update(params, state, grid)
-        projection_remap(params, state, grid)
+        for step, label in ((update_EOS, "EOS"), (block_ghost_exchange, "boundary_conditions"),
+                            (numerical_fluxes, "numerical_fluxes"), (cell_update, "cell_update"),
+                            (projection_remap, "projection_remap")):
+            step(params, state, grid)
+            if checkpoint(label):
+                return True
     return False
 
 

@@ -85,3 +85,25 @@ def test_output_format_round_trip_on_a_stub_grid(golden):
         assert np.array_equal(data[v], ref[v]), v                        # 17 significant digits round-trip exactly
     for v in ("x", "y"):                                                 # coordinates recomputed like the init kernel
         assert np.allclose(data[v], ref[v], rtol=0, atol=1e-15), v
+
+
+def test_compare_data_and_time_step_files(tmp_path):
+    """compare_block's isapprox rule and report, the time-step checkpoint file (src/io.jl:88-168), without a GPU."""
+    import numpy as np
+    import armon_jl_b200 as armon
+    from armon_jl_b200.io import compare_data, read_time_step_file, write_time_step_file
+    p = armon.ArmonParameters(test="Sod", N=(6, 4), output_dir=str(tmp_path), comparison_tolerance=1e-10, silent=5)
+    write_time_step_file(p, 0.0043196268869671031, "dt_000")
+    assert (tmp_path / "dt_000").read_text() == " 4.31962688696710308e-03\n"       # "%#24.17e"
+    assert read_time_step_file(p, "dt_000") == 0.0043196268869671031
+    base = {v: np.arange(24, dtype=np.float64).reshape(4, 6) + 1.0 for v in ("x", "y", "rho", "u", "v", "p")}
+    other = {v: a.copy() for v, a in base.items()}
+    lines = []
+    assert not compare_data(p, base, other, "cell_update", out=lines.append) and not lines
+    other["rho"][2, 3] *= 1 + 1e-9          # beyond rtol
+    other["u"][0, 0] *= 1 + 1e-12           # within rtol
+    other["p"][1, 1] = np.nan
+    assert compare_data(p, base, other, "cell_update", out=lines.append)
+    assert lines[0] == "At cell_update, in block (1, 1):"
+    assert lines[1] == "  1 differences found in rho (ref ≢ current)" and "(  4,  3 |   4,  3)" in lines[2]
+    assert any("1 differences found in p" in ln for ln in lines) and not any("found in u" in ln for ln in lines)
