@@ -450,8 +450,8 @@ def test_output_file_round_trip(tmp_path, golden):
 
 def test_compare_is_ref_checkpoint_protocol(tmp_path, capsys):
     """`compare=true` step checkpoints (src/io.jl:185-227): a reference run leaves one file per step, an identical run
-    compares clean against them, a run with another limiter stops at the first `numerical_fluxes` checkpoint, and an
-    oracle-written reference (the CPU path's values) is accepted step by step by the B200 per-step kernels."""
+    compares clean against them, a run with another limiter stops at the first checkpoint whose saved variables differ
+    and leaves the `_diff` file."""
     from armon_jl_b200.io import step_checkpoint, write_sub_domain_file
     kw = dict(N=(40, 30), maxcycle=3, output_dir=str(tmp_path), output_file="chk", compare=True, silent=5)
     ref = armon.armon(reference_params("Sod_circ", is_ref=True, return_data=True, **kw))
@@ -459,7 +459,8 @@ def test_compare_is_ref_checkpoint_protocol(tmp_path, capsys):
     files = sorted(p.name for p in tmp_path.iterdir())
     assert "chk_000_init_test_X" in files and "chk_000_time_step_X" in files and "chk_002_projection_remap_Y" in files
     assert len(files) == 2 + 3 * (1 + 2 * 5)        # init_test, EOS_init + per cycle: time_step + 2 axes x 5 steps
-    assert len((tmp_path / "chk_001_time_step_X").read_text().strip()) == 24
+    # the axis letter of a time_step checkpoint is the axis of the previous sweep (X only before the first cycle)
+    assert len((tmp_path / "chk_001_time_step_Y").read_text().strip()) == 23
     ref.data.close()
 
     same = armon.armon(reference_params("Sod_circ", is_ref=False, return_data=True, **kw))
@@ -468,6 +469,8 @@ def test_compare_is_ref_checkpoint_protocol(tmp_path, capsys):
 
     other = armon.armon(reference_params("Sod_circ", is_ref=False, return_data=True, riemann_limiter="superbee", **kw))
     out = capsys.readouterr().out
-    assert other.cycles == 0 and "At numerical_fluxes" in out and "Difference file written to chk_000_numerical_fluxes_X_diff" in out
-    assert (tmp_path / "chk_000_numerical_fluxes_X_diff").exists()
+    # the saved variables (x, y, rho, u, v, p) first feel the limiter in a cell_update of cycle 0: the run stops there
+    assert other.cycles == 0 and "At cell_update, in block (1, 1):" in out and "differences found in rho (ref ≢ current)" in out
+    diff = [p.name for p in tmp_path.iterdir() if p.name.endswith("_diff")]
+    assert len(diff) == 1 and diff[0].startswith("chk_000_cell_update_") and f"Difference file written to {diff[0]}" in out
     other.data.close()
