@@ -80,7 +80,9 @@ end
 function Armon.create_device(::Val{:B200})
     flt = ccall((:armon_flt_size, LIB), Cint, ())       # ABI self-check, cf. ext/ArmonKokkos.jl:122-140
     idx = ccall((:armon_idx_size, LIB), Cint, ())
-    (flt == 8 && idx == 8) || solver_error(:config, "libarmon_b200 ABI mismatch (flt=$flt, idx=$idx)")
+    abi = ccall((:armon_b200_abi_version, LIB), Cint, ())
+    (flt == 8 && idx == 8 && abi == 2) ||
+        solver_error(:config, "libarmon_b200 ABI mismatch (flt=$flt, idx=$idx, abi=$abi): this file binds ABI version 2")
     CURRENT_DEVICE[] = B200Device()
 end
 Armon.device_array_type(::B200Device) = B200Array
@@ -89,13 +91,31 @@ Armon.host_array_type(::B200Device) = Array
 # backend_options: the fused solver handle + what it was built from
 mutable struct B200Options
     solver::Ptr{Cvoid}
-    math_mode::Cint
+    math_mode::Cint      # ARMON_MATH_*: 0 strict (bit-exact vs the CPU path compiled without @fastmath), 1 fast, 2 ieee
+    kernel_variant::Cint # ARMON_KERNEL_*: 0 auto
+    cuda_graph::Cint     # 0 auto (grids <= 512^2 on one rank), 1 on, 2 off
     dirty::Bool          # device state not yet brought back to the canonical layout (armon_solver_finalize)
 end
 
-function Armon.init_backend(params::ArmonParameters, ::B200Device; math_mode = :strict, options...)
-    params.backend_options = B200Options(C_NULL, math_mode === :fast ? 1 : math_mode === :ieee ? 2 : 0, false)
+const KERNEL_VARIANTS = Dict(:auto => 0, :single => 1, :async => 4, :async2 => 5, :tma => 6)
+const CUDA_GRAPH_MODES = Dict(:auto => 0, :on => 1, :off => 2)
+
+function Armon.init_backend(params::ArmonParameters, ::B200Device;
+                            math_mode = :strict, kernel_variant = :auto, cuda_graph = :auto, options...)
+    params.backend_options = B200Options(C_NULL, math_mode === :fast ? 1 : math_mode === :ieee ? 2 : 0,
+                                         KERNEL_VARIANTS[kernel_variant], CUDA_GRAPH_MODES[cuda_graph], false)
     return options
+end
+
+# Every reader of the bound arrays (device_to_host!, conservation_vars, dtCFL_kernel, the per-step kernels) must first
+# bring the fused solver's rotating, possibly transposed buffers back to the canonical BlockData layout (+ stale p, c, g).
+function ensure_canonical(params::ArmonParameters)
+    opts = params.backend_options
+    if opts.dirty && opts.solver != C_NULL
+        @b200call(:armon_solver_finalize, (Ptr{Cvoid},), opts.solver)
+        opts.dirty = false
+    end
+    return nothing
 end
 
 Base.wait(params::ArmonParameters{<:Any, <:B200Device}) =
@@ -134,11 +154,15 @@ struct CSolverDesc
     cfl::Float64; maxtime::Float64; maxcycle::Int64
     cst_dt::Int32; Dt::Float64
     neighbours::NTuple{4, Int32}
-    math_mode::Int32; march_segment::Int32; kernel_variant::Int32
+    math_mode::Int32; march_segment::Int32; kernel_variant::Int32; cuda_graph::Int32
     tc::CTestCase
 end
 struct CTimeState
     cycle::Int64; time::Float64; current_dt::Float64; next_cycle_dt::Float64; error::Int32; done::Int32
+    error_cycle::Int64
+end
+struct CCycleDiag   # armon_cycle_diag: one line of the `silent <= 1` log (src/solver.jl:359-371), produced on the device
+    cycle::Int64; time::Float64; dt::Float64; mass::Float64; energy::Float64
 end
 
 test_code(::Armon.Sod) = 0; test_code(::Armon.Sod_y) = 1; test_code(::Armon.Sod_circ) = 2
@@ -169,7 +193,8 @@ function c_solver_desc(params::ArmonParameters{T}, state::SolverState) where {T}
                 riemann_code(state.riemann_scheme), limiter_code(state.riemann_limiter),
                 projection_code(state.projection_scheme), splitting_code(state.splitting),
                 params.cfl, params.maxtime, params.maxcycle, params.cst_dt, params.Dt, nb,
-                params.backend_options.math_mode, 0, 0, c_test_case(params))
+                params.backend_options.math_mode, 0, params.backend_options.kernel_variant,
+                params.backend_options.cuda_graph, c_test_case(params))
 end
 
 # ------------------------------------------------------------------------------------------------------------
@@ -218,19 +243,40 @@ end
 function Armon.next_cycle!(params::ArmonParameters{<:Any, <:B200Device}, global_dt::Armon.GlobalTimeStep)
     st = Ref{CTimeState}()
     @b200call(:armon_solver_state, (Ptr{Cvoid}, Ptr{CTimeState}), params.backend_options.solver, st)
-    st[].error == 4 && solver_error(:time, "Invalid time step for cycle $(st[].cycle)")
+    st[].error == 4 && solver_error(:time, "Invalid time step for cycle $(st[].error_cycle)")
+    st[].error == 6 && solver_error(:cpp, "cycle $(st[].error_cycle): the strict mode's IEEE fix-up list overflowed; use math_mode=:ieee")
     global_dt.cycle, global_dt.time = st[].cycle, st[].time
     global_dt.current_dt, global_dt.next_cycle_dt = st[].current_dt, st[].next_cycle_dt
 end
 
 # device_to_host!(grid), src/blocking/block_grid.jl:717-729: canonical layout + stale p, c, g first
 function Armon.device_to_host!(grid::BlockGrid{<:Any, <:B200Array})
-    params = grid.params
-    if params.backend_options.dirty
-        @b200call(:armon_solver_finalize, (Ptr{Cvoid},), params.backend_options.solver)
-        params.backend_options.dirty = false
-    end
+    ensure_canonical(grid.params)
     invoke(Armon.device_to_host!, Tuple{BlockGrid}, grid)
+end
+
+# time_loop(params, grid), src/solver.jl:323-403, when nothing needs the host between cycles (silent > 1, no animation):
+# the whole `while time < maxtime && cycle < maxcycle` runs on the device.  With silent <= 1 on one rank the per-cycle
+# log is produced on the device too (armon_solver_diagnostics) and printed when the loop returns.
+function device_time_loop(params::ArmonParameters{<:Any, <:B200Device}, grid::BlockGrid)
+    solver = fused_solver(params, grid)
+    verbose = params.silent <= 1 && !(params.use_MPI && params.proc_size > 1)
+    verbose && @b200call(:armon_solver_diagnostics, (Ptr{Cvoid}, Int32), solver, min(params.maxcycle + 1, 1 << 20))
+    @b200call(:armon_solver_time_loop, (Ptr{Cvoid},), solver)
+    params.backend_options.dirty = true
+    if verbose
+        lines = Vector{CCycleDiag}(undef, 4096); n = Ref{Int64}(0)
+        while true
+            @b200call(:armon_solver_read_diagnostics, (Ptr{Cvoid}, Ptr{CCycleDiag}, Int64, Ptr{Int64}), solver, lines, length(lines), n)
+            n[] == 0 && break
+            for l in view(lines, 1:n[])
+                ΔM = abs(params.initial_mass - l.mass) / params.initial_mass * 100
+                ΔE = abs(params.initial_energy - l.energy) / params.initial_energy * 100
+                Armon.@printf("Cycle %4d: dt = %.18f, t = %.18f, |ΔM| = %#8.6g%%, |ΔE| = %#8.6g%%\n", l.cycle, l.dt, l.time, ΔM, ΔE)
+            end
+        end
+        @b200call(:armon_solver_diagnostics, (Ptr{Cvoid}, Int32), solver, 0)
+    end
 end
 
 # ------------------------------------------------------------------------------------------------------------
@@ -317,6 +363,7 @@ end
 
 # dtCFL_kernel(params, state, blk, ΔX), src/reductions.jl:65-88: returns the host value like `mapreduce`
 function Armon.dtCFL_kernel(params::B200Params, ::SolverState, blk::LocalTaskBlock, ΔX)
+    ensure_canonical(params)
     d = Armon.block_device_data(blk)
     res = Ref{Float64}(Inf)
     @b200call(:armon_dtCFL, (Ptr{Cvoid}, CDims, PF, PF, PF, Float64, Float64, Ptr{Float64}),
@@ -326,6 +373,7 @@ end
 
 # conservation_vars(params, blk), src/reductions.jl:271-298 -> (mass, energy) of the block
 function Armon.conservation_vars(params::B200Params, blk::LocalTaskBlock)
+    ensure_canonical(params)
     d = Armon.block_device_data(blk)
     ds = prod(params.domain_size ./ params.global_grid)
     mass, energy = Ref{Float64}(0), Ref{Float64}(0)
