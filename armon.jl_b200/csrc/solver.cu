@@ -356,6 +356,12 @@ struct armon_solver {
     sweep_fast_fn_t   fast_kernel[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     bool              use_fast = false;
     int               fast_stg = STG_TMA;
+    sweep_fast_fn_t   fast_cons_kernel[2] = {nullptr, nullptr};   // TMA staging + conservation sums, [transposed output]
+    // per-cycle diagnostics: this block's region of the group's partial-sum scratch, and whether the last sweep of the
+    // cycle being enqueued filled it itself (fused) or k_diag_rows has to
+    long long         diag_base = 0, diag_cap = 0;
+    double           *cons_m = nullptr, *cons_e = nullptr;   // set by group_sweep for the last sweep of a cycle
+    bool              cons_done = false;
     std::map<std::tuple<const double *, long long, long long>, CUtensorMap> tmaps;   // (array, rows, pitch) -> tensor map
     bool              overlap = true;          // interior / edge split of a sweep around the halo exchange (ARMON_B200_OVERLAP=0 disables)
     unsigned         *fix_count = nullptr;     // two counters, used alternately by successive sweeps
@@ -658,6 +664,11 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     } else {
         memset(&maps, 0, sizeof(maps));
     }
+    // per-cycle diagnostics: the last sweep of the cycle accumulates the conservation sums itself when it can
+    const bool cons = fast_launch && stg == STG_TMA && s->cons_m != nullptr && s->fast_cons_kernel[A.transpose_out ? 1 : 0];
+    A.cons_m = cons ? s->cons_m : nullptr;
+    A.cons_e = cons ? s->cons_e : nullptr;
+    s->cons_done = cons;
     const bool staged_launch = !fast_launch && s->use_staged && (A.pitch_in % 2) == 0;
     const long long cols_per_cta = (staged_launch || fast_launch) ? ASYNC_TPB : SWEEP_TPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -689,7 +700,8 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         A.y_jump = (int)y_jump;
         const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
         if (fast_launch)
-            s->fast_kernel[stg][A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
+            (cons ? s->fast_cons_kernel[A.transpose_out ? 1 : 0] : s->fast_kernel[stg][A.transpose_out ? 1 : 0])
+                <<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
         else if (staged_launch)
             s->staged_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->staged_smem, st>>>(A);
         else
@@ -745,11 +757,16 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
 }
 
 // One axis sweep of every block of the group, in lock step.
-int group_sweep(armon_group *G, int axis, double dt_factor, int acc_slot, int next_axis)
+int group_sweep(armon_group *G, int axis, double dt_factor, int acc_slot, int next_axis, bool last_of_cycle)
 {
     NvtxRange r(axis == ARMON_AXIS_X ? "X" : "Y");
-    for (armon_solver *b : G->blocks)
+    for (armon_solver *b : G->blocks) {
         if (int rc = ensure_layout(b, axis)) return rc;
+        const bool diag = last_of_cycle && G->diag_ring != nullptr;
+        b->cons_m = diag ? G->diag_rows + b->diag_base : nullptr;
+        b->cons_e = diag ? G->diag_rows + G->diag_rows_cap + b->diag_base : nullptr;
+        b->cons_done = false;
+    }
     if (G->blocks.size() > 1) {
         NvtxRange r2("BC");
         for (armon_solver *b : G->blocks)
@@ -846,19 +863,19 @@ int launch_diagnostics(armon_group *G)
     if (!G->diag_ring) return ARMON_OK;
     NvtxRange r("conservation_vars");
     const armon_solver_desc &d0 = G->blocks[0]->d;
-    long long off = 0;
     double *row_m = G->diag_rows, *row_e = G->diag_rows + G->diag_rows_cap;
     for (armon_solver *b : G->blocks) {
+        if (b->cons_done) continue;   // the last sweep left one partial per warp in the block's region
         const armon_dims &D = b->d.dims;
         const long long n_rows = b->cur_transposed ? D.nx : D.ny, n_cols = b->cur_transposed ? D.ny : D.nx;
         const unsigned nblk = (unsigned)(n_rows < 4096 ? n_rows : 4096);
         k_diag_rows<<<nblk, TPB, 0, G->ctx->stream>>>(n_rows, n_cols, n_cols + 2 * D.g, (int)D.g, b->buf[b->cur][0],
-                                                      b->buf[b->cur][3], row_m + off, row_e + off);
+                                                      b->buf[b->cur][3], row_m + b->diag_base, row_e + b->diag_base);
         ARMON_LAUNCH_CHECK(G->ctx);
-        off += n_rows;
     }
     const double ds = (d0.domain_size[0] / (double)d0.global_nx) * (d0.domain_size[1] / (double)d0.global_ny);
-    k_diag_final<<<1, TPB, 0, G->ctx->stream>>>(off, row_m, row_e, ds, G->ts, G->diag_ring, G->diag_head, G->diag_cap);
+    k_diag_final<<<1, TPB, 0, G->ctx->stream>>>(G->diag_rows_cap, row_m, row_e, ds, G->ts, G->diag_ring, G->diag_head,
+                                                G->diag_cap);
     ARMON_LAUNCH_CHECK(G->ctx);
     return ARMON_OK;
 }
@@ -876,6 +893,8 @@ int enqueue_cycle(armon_group *G)
         if (int rc = launch_cycle_step(G, true, 1, true)) return rc;
         G->started = true;
     }
+    if (G->diag_ring)   // partial sums of this cycle's log line: unused slots must read 0
+        ARMON_CUDA(cudaMemsetAsync(G->diag_rows, 0, (size_t)(2 * G->diag_rows_cap) * sizeof(double), G->ctx->stream));
     int axes[3], next_axes[3];
     double factors[3], next_factors[3];
     const long long k = G->host_cycle;
@@ -884,7 +903,7 @@ int enqueue_cycle(armon_group *G)
     for (int i = 0; i < n; i++) {
         const bool last = i == n - 1;
         const int next_axis = last ? next_axes[0] : axes[i + 1];
-        if (int rc = group_sweep(G, axes[i], factors[i], last ? (int)(k & 1) : 2, next_axis)) return rc;
+        if (int rc = group_sweep(G, axes[i], factors[i], last ? (int)(k & 1) : 2, next_axis, last)) return rc;
     }
     {
         NvtxRange r2("time_step");
@@ -1101,8 +1120,21 @@ int group_diagnostics(armon_group *G, int32_t capacity)
     G->diag_cap = 0;
     G->diag_read = 0;
     if (capacity == 0) return ARMON_OK;
+    // per block: one partial per array row (k_diag_rows) or per warp of the last sweep (fused), whichever is larger
     long long rows = 0;
-    for (const armon_solver *b : G->blocks) rows += b->d.dims.nx > b->d.dims.ny ? b->d.dims.nx : b->d.dims.ny;
+    for (armon_solver *b : G->blocks) {
+        const armon_dims &D = b->d.dims;
+        long long cap = D.nx > D.ny ? D.nx : D.ny;
+        for (int axis = 0; axis < 2; axis++) {
+            const long long nm = axis == ARMON_AXIS_X ? D.nx : D.ny, nw = axis == ARMON_AXIS_X ? D.ny : D.nx;
+            const long long seg = pick_segment(b, nm, nw);
+            const long long parts = ((nm + seg - 1) / seg) * ((nw + ASYNC_TPB - 1) / ASYNC_TPB) * (ASYNC_TPB / 32);
+            cap = parts > cap ? parts : cap;
+        }
+        b->diag_base = rows;
+        b->diag_cap = cap;
+        rows += cap;
+    }
     ARMON_CUDA(cudaMalloc(&G->diag_ring, (size_t)capacity * sizeof(armon_cycle_diag)));
     ARMON_CUDA(cudaMalloc(&G->diag_head, sizeof(unsigned long long)));
     ARMON_CUDA(cudaMalloc(&G->diag_rows, (size_t)(2 * rows) * sizeof(double)));
@@ -1209,6 +1241,16 @@ int select_kernels(armon_solver *s)
                 }
             }
         s->use_fast = ok;
+        for (int tr = 0; tr < 2 && ok; tr++) {
+            sweep_fast_fn_t fn = biz ? sweep_fast_table_tma_cons_biz(rl, desc->projection, tr)
+                                     : sweep_fast_table_tma_cons_pg(rl, desc->projection, tr);
+            s->fast_cons_kernel[tr] = fn;
+            if (!fn) continue;
+            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(ASYNC_TPB / 32 * sizeof(FastWarpShared))));
+            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+        }
     }
     if (variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT) {
         bool ok = true;

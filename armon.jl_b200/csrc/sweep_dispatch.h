@@ -80,17 +80,20 @@ sweep_fast_fn_t sweep_fast_table_cpa16_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_cpa16_biz(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_cpa8_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_cpa8_biz(int rl, int proj, int tr);
+// TMA staging + conservation sums (the last sweep of a cycle when the per-cycle diagnostics are on)
+sweep_fast_fn_t sweep_fast_table_tma_cons_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_tma_cons_biz(int rl, int proj, int tr);
 
-#define ARMON_FAST_ROW(STG, RLV, EOS)                                                        \
-    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
-     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1>}}
+#define ARMON_FAST_ROW(STG, RLV, EOS, CONS)                                                  \
+    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS>}, \
+     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS>}}
 
-#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS)                                              \
+#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS)                                        \
     sweep_fast_fn_t NAME(int rl, int proj, int tr)                                          \
     {                                                                                       \
         static const sweep_fast_fn_t table[4][2][2] = {                                     \
-            ARMON_FAST_ROW(STG, 0, EOS), ARMON_FAST_ROW(STG, 1, EOS),                       \
-            ARMON_FAST_ROW(STG, 2, EOS), ARMON_FAST_ROW(STG, 3, EOS),                       \
+            ARMON_FAST_ROW(STG, 0, EOS, CONS), ARMON_FAST_ROW(STG, 1, EOS, CONS),           \
+            ARMON_FAST_ROW(STG, 2, EOS, CONS), ARMON_FAST_ROW(STG, 3, EOS, CONS),           \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \

@@ -196,7 +196,7 @@ struct FastIter {
 // One march step at cell a; J = (a - a_begin) & 3 static.  EMIT / TR compile-time as in march_compute2; `ok`: the
 // thread's column holds a real cell (false also for the steps that run the emitting code on cells before the segment,
 // see the kernel).
-template <int RL, int PROJ, int EOS, int J, int TR, int EMIT>
+template <int RL, int PROJ, int EOS, int J, int TR, int EMIT, int CONS>
 __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, PipeF &P, const FastIter &I,
                                           const double dt, const bool ok)
 {
@@ -312,6 +312,10 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
             const unsigned long long bt = (unsigned long long)__double_as_longlong(xadd(fabs(o_ut), c_out));
             T.amax = (store && ba > T.amax) ? ba : T.amax;
             T.tmax = (store && bt > T.tmax) ? bt : T.tmax;
+        }
+        if (CONS && store) {   // conservation_vars (src/reductions.jl:202-259) of the state this sweep produces
+            T.cm = xadd(T.cm, o_r);
+            T.ce = xfma(o_r, o_E, T.ce);
         }
         if (TR == 1) {
             double *s = J == 3 ? I.s3 : I.s0 + J;
@@ -463,7 +467,9 @@ __device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
 #define FAST_MIN_BLOCKS (256 / ASYNC_TPB_VALUE)   // 8 warps per SM
 #endif
 
-template <int STG, int RL, int PROJ, int EOS, int TR>
+// CONS = 1: also accumulates the conservation sums of the cells it stores (per-cycle diagnostics fused into the last
+// sweep of a cycle): per thread in march order, per warp by a fixed butterfly, one partial per warp for k_diag_final.
+template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0>
 __global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
 sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 {
@@ -486,9 +492,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     T.valid = w < A.nw;
     T.col = (T.valid ? w : A.nw - 1) + A.g;
     T.amax = 0ULL; T.tmax = 0ULL;
+    T.cm = 0.0; T.ce = 0.0;
+    const long long cons_slot = (kseg * gridDim.x + blockIdx.x) * (ASYNC_TPB / 32) + warp;
 
     const DeviceTimeState *ts = A.ts;
     if (ts->done) {   // see sweep_kernel: copy the state through so that the host's buffer rotation stays valid
+        if (CONS && lane == 0) { A.cons_m[cons_slot] = 0.0; A.cons_e[cons_slot] = 0.0; }   // the log line is dropped anyway
         if (T.valid) {
             for (long long m = m_lo; m < m1; m++) {
                 const long long i = (m + A.g) * A.pitch_in + T.col;
@@ -499,7 +508,10 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         }
         return;
     }
-    if (w0 >= A.nw) return;   // warp entirely outside the domain (warps are independent: no CTA barrier below)
+    if (w0 >= A.nw) {   // warp entirely outside the domain (warps are independent: no CTA barrier below)
+        if (CONS && lane == 0) { A.cons_m[cons_slot] = 0.0; A.cons_e[cons_slot] = 0.0; }
+        return;
+    }
 
     const double dt = xmul(ts->current_dt, A.dt_factor);   // update_solver_state!, src/solver_state.jl:339-345
     const int len = (int)(m1 - m0);
@@ -608,7 +620,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     I.gb1 = ring + (FK_NG - 1) * FK_GS;   // "group -1": benign
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
-#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv>(A, T, P, I, dt, OK);
+#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS>(A, T, P, I, dt, OK);
 #define FK_BEGIN(it)                                                                                        \
     {                                                                                                       \
         const int p_ = (it) & 1;                                                                            \
@@ -676,5 +688,14 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     if (lane == 0) {
         atomicMax(&A.ts->acc[A.acc_slot][0], am);
         atomicMax(&A.ts->acc[A.acc_slot][1], tm);
+    }
+    if (CONS) {
+        double cm = T.cm, ce = T.ce;   // 0 in the lanes without a real column
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {   // fixed butterfly: both lanes of a pair form the same sum
+            cm = xadd(cm, __shfl_xor_sync(0xffffffffu, cm, off));
+            ce = xadd(ce, __shfl_xor_sync(0xffffffffu, ce, off));
+        }
+        if (lane == 0) { A.cons_m[cons_slot] = cm; A.cons_e[cons_slot] = ce; }
     }
 }

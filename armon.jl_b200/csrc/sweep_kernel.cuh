@@ -61,6 +61,9 @@ struct SweepArgs {
     unsigned long long *fix_list;
     unsigned fix_cap;       // capacity of fix_list (entries); an overflow raises ARMON_ERR_RANGE
     int fix_rows;           // 0: an entry is (segment << 32 | column); > 0: (first row << 32 | column), fix_rows rows
+    // per-cycle diagnostics fused into the last sweep of a cycle (sweep_fast_kernel<..., CONS = 1>): one partial
+    // (sum rho, sum rho*E) per warp, slot (segment * gridDim.x + blockIdx.x) * warps per CTA + warp
+    double *cons_m, *cons_e;
 };
 
 // index of the march segment of this CTA: a sweep is one launch over all segments, or -- when the ghost rows of a
@@ -130,6 +133,7 @@ struct SweepThread {
     bool      valid;       // column holds a real cell
     const double *base[4]; // A.in[k] + col
     unsigned long long amax, tmax;   // dt accumulators (integer images of non-negative doubles)
+    double cm, ce;         // conservation sums of the cells this thread stored: sum rho, sum rho*E (fast kernel, CONS)
     RangeFlag flag;        // range bookkeeping of the branch-free divisions (DIV_FLAGGED)
 };
 
