@@ -80,6 +80,8 @@ SIGNATURES = {
     "armon_copy_h2d": [_VP, _VP, _VP, C.c_uint64],
     "armon_copy_d2h": [_VP, _VP, _VP, C.c_uint64],
     "armon_copy_d2d": [_VP, _VP, _VP, C.c_uint64],
+    "armon_copy_h2d_f32": [_VP, _VP, _VP, C.c_uint64],
+    "armon_copy_d2h_f32": [_VP, _VP, _VP, C.c_uint64],
     "armon_fill": [_VP, _VP, C.c_double, C.c_uint64],
     "armon_fill_ghosts": [_VP, armon_dims, _VP, C.c_double],
     "armon_perfect_gas_EOS": _DIMS_DOM + [C.c_double] + [_VP] * 7,
@@ -294,16 +296,23 @@ class B200Array:
         return self.n
 
     def copy_from_host(self, host):
-        host = np.ascontiguousarray(host, dtype=np.float64).reshape(-1)
+        """copyto!(device, host): Float64 arrays as they are, Float32 arrays (`ArmonParameters{Float32}`) widened on
+        the device -- the device side is always Float64."""
+        host = np.asarray(host)
+        f32 = host.dtype == np.float32
+        host = np.ascontiguousarray(host, dtype=np.float32 if f32 else np.float64).reshape(-1)
         if host.size != self.n:
             raise ValueError(f"size mismatch: {host.size} != {self.n}")
-        check(self.device.lib.armon_copy_h2d(self.device.ctx, self._ptr, host.ctypes.data_as(_VP), self.n))
+        fn = self.device.lib.armon_copy_h2d_f32 if f32 else self.device.lib.armon_copy_h2d
+        check(fn(self.device.ctx, self._ptr, host.ctypes.data_as(_VP), self.n))
 
-    def copy_to_host(self, out=None):
+    def copy_to_host(self, out=None, dtype=np.float64):
+        """copyto!(host, device); a Float32 destination receives the values rounded to nearest."""
         if out is None:
-            out = np.empty(self.n, dtype=np.float64)
-        assert out.dtype == np.float64 and out.size == self.n and out.flags["C_CONTIGUOUS"]
-        check(self.device.lib.armon_copy_d2h(self.device.ctx, out.ctypes.data_as(_VP), self._ptr, self.n))
+            out = np.empty(self.n, dtype=dtype)
+        assert out.dtype in (np.float64, np.float32) and out.size == self.n and out.flags["C_CONTIGUOUS"]
+        fn = self.device.lib.armon_copy_d2h_f32 if out.dtype == np.float32 else self.device.lib.armon_copy_d2h
+        check(fn(self.device.ctx, out.ctypes.data_as(_VP), self._ptr, self.n))
         return out
 
     def fill(self, value):

@@ -267,7 +267,7 @@ class BlockGrid:
         self.finalize()
         for name in vars:
             if all(name in b.device_data.allocated() for b in self.blocks):
-                self.host_data[name] = self.host_array(name)
+                self.host_data[name] = self.host_array(name)      # in the caller's type (params.dtype)
         return self.host_data
 
     def host_to_device(self, vars=None):
@@ -279,11 +279,12 @@ class BlockGrid:
         """Full [ny+2g, nx+2g] host copy of one variable (fresh read-back).  With several blocks the frame of ghost
         cells comes from the blocks on the edge of the sub-domain; real cells always from the block that owns them."""
         self.finalize()
+        T = self.params.dtype
         if not self.multi:
-            return getattr(self.blocks[0].device_data, name).copy_to_host().reshape(self.shape)
+            return getattr(self.blocks[0].device_data, name).copy_to_host(dtype=T).reshape(self.shape)
         g = self.params.nghost
-        out = np.empty(self.shape, dtype=np.float64)
-        parts = [(b, getattr(b.device_data, name).copy_to_host().reshape(b.shape)) for b in self.blocks]
+        out = np.empty(self.shape, dtype=T)
+        parts = [(b, getattr(b.device_data, name).copy_to_host(dtype=T).reshape(b.shape)) for b in self.blocks]
         for b, a in parts:      # ghosts included first ...
             out[b.offset[1]:b.offset[1] + b.shape[0], b.offset[0]:b.offset[0] + b.shape[1]] = a
         for b, a in parts:      # ... then every real cell from its owner
@@ -296,7 +297,8 @@ class BlockGrid:
 
     def set_array(self, name, values):
         self.finalize()
-        values = np.asarray(values, dtype=np.float64).reshape(self.shape)
+        values = np.asarray(values)
+        values = values.astype(np.float64 if values.dtype != np.float32 else np.float32, copy=False).reshape(self.shape)
         for b in self.blocks:   # every block receives its window of the array, ghosts included
             win = values[b.offset[1]:b.offset[1] + b.shape[0], b.offset[0]:b.offset[0] + b.shape[1]]
             getattr(b.device_data, name).copy_from_host(np.ascontiguousarray(win))

@@ -7,6 +7,16 @@
 namespace {
 thread_local char g_last_error[1024] = "";
 constexpr size_t SCRATCH_ELEMS = 2 + 2 * 65536;   // reduction scratch: 2 results + two per-row partial arrays
+constexpr size_t STAGE_F32_ELEMS = 8u << 20;      // 32 MB of Float32 staging per chunk
+
+__global__ void k_widen(double *dst, const float *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+__global__ void k_narrow(float *dst, const double *src, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __double2float_rn(src[i]);
+}
 }   // namespace
 
 void armon_set_error(const char *fmt, ...)
@@ -82,6 +92,7 @@ int armon_ctx_destroy(armon_ctx *ctx)
     // communicator (garbage collection, error paths: not synchronised across ranks) aborts it instead of blocking.
     if (ctx->comm) { ncclCommAbort(ctx->comm); ctx->comm = nullptr; }
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage_f32) cudaFree(ctx->stage_f32);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -166,6 +177,36 @@ int armon_copy_d2d(armon_ctx *ctx, double *dst_dev, const double *src_dev, uint6
     ARMON_CHECK_ARG(ctx && dst_dev && src_dev, "null argument");
     if (int rc = armon_ctx_activate(ctx)) return rc;
     ARMON_CUDA(cudaMemcpyAsync(dst_dev, src_dev, n_elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ARMON_OK;
+}
+
+int armon_copy_h2d_f32(armon_ctx *ctx, double *dst_dev, const float *src_host, uint64_t n_elems)
+{
+    ARMON_CHECK_ARG(ctx && dst_dev && src_host, "null argument");
+    if (int rc = armon_ctx_activate(ctx)) return rc;
+    if (!ctx->stage_f32) ARMON_CUDA(cudaMalloc(&ctx->stage_f32, STAGE_F32_ELEMS * sizeof(float)));
+    for (uint64_t off = 0; off < n_elems; off += STAGE_F32_ELEMS) {
+        const size_t n = (size_t)(n_elems - off < STAGE_F32_ELEMS ? n_elems - off : STAGE_F32_ELEMS);
+        ARMON_CUDA(cudaMemcpyAsync(ctx->stage_f32, src_host + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        k_widen<<<148 * 8, 256, 0, ctx->stream>>>(dst_dev + off, ctx->stage_f32, n);
+        ARMON_LAUNCH_CHECK(ctx);
+        ARMON_CUDA(cudaStreamSynchronize(ctx->stream));   // the staging buffer and the host buffer may be reused right away
+    }
+    return ARMON_OK;
+}
+
+int armon_copy_d2h_f32(armon_ctx *ctx, float *dst_host, const double *src_dev, uint64_t n_elems)
+{
+    ARMON_CHECK_ARG(ctx && dst_host && src_dev, "null argument");
+    if (int rc = armon_ctx_activate(ctx)) return rc;
+    if (!ctx->stage_f32) ARMON_CUDA(cudaMalloc(&ctx->stage_f32, STAGE_F32_ELEMS * sizeof(float)));
+    for (uint64_t off = 0; off < n_elems; off += STAGE_F32_ELEMS) {
+        const size_t n = (size_t)(n_elems - off < STAGE_F32_ELEMS ? n_elems - off : STAGE_F32_ELEMS);
+        k_narrow<<<148 * 8, 256, 0, ctx->stream>>>(ctx->stage_f32, src_dev + off, n);
+        ARMON_LAUNCH_CHECK(ctx);
+        ARMON_CUDA(cudaMemcpyAsync(dst_host + off, ctx->stage_f32, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        ARMON_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     return ARMON_OK;
 }
 

@@ -73,9 +73,15 @@ class ArmonParameters:
     """
 
     def __init__(self, *, data_type="Float64", N=(10, 10), **options):
-        if str(data_type).lstrip(":") not in ("Float64", "float64", "<class 'float'>"):
-            solver_error("config", f"the B200 backend computes in Float64 only, got data_type={data_type}")
-        self.data_type = "Float64"
+        # ArmonParameters{T}: T is the type of the caller's arrays.  The device arrays and all arithmetic are Float64
+        # for both; with Float32 the conversion happens in the host <-> device copies (armon_copy_*_f32).
+        name = str(data_type).lstrip(":")
+        if name in ("Float64", "float64", "<class 'float'>", "<class 'numpy.float64'>"):
+            self.data_type = "Float64"
+        elif name in ("Float32", "float32", "<class 'numpy.float32'>"):
+            self.data_type = "Float32"
+        else:
+            solver_error("config", f"the B200 backend supports Float64 and Float32 (computed in Float64), got data_type={data_type}")
         self.N = tuple(int(n) for n in N)
         if len(self.N) != 2:
             solver_error("config", f"Expected a 2D domain, got N={N}")
@@ -205,7 +211,8 @@ class ArmonParameters:
         self.silent = int(silent)
         self.output_dir, self.output_file = output_dir, output_file
         self.write_output, self.write_ghosts, self.write_slices = bool(write_output), bool(write_ghosts), bool(write_slices)
-        self.output_precision = 17 if output_precision is None else int(output_precision)
+        # exact decimal output by default (src/parameters.jl:708-710)
+        self.output_precision = (17 if self.data_type == "Float64" else 9) if output_precision is None else int(output_precision)
         self.animation_step = int(animation_step)
         self.compare, self.is_ref = bool(compare), bool(is_ref)
         self.comparison_tolerance = float(comparison_tolerance)
@@ -280,6 +287,12 @@ class ArmonParameters:
         return out
 
     # -- helpers ---------------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        """numpy dtype of the host-side arrays: `data_type(params)`"""
+        import numpy as np
+        return np.float32 if self.data_type == "Float32" else np.float64
+
     def cell_size(self):
         """ΔX = domain_size ./ global_grid (src/kernels.jl:184, src/reductions.jl:92)"""
         return tuple(d / n for d, n in zip(self.domain_size, self.global_grid))

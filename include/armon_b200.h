@@ -167,6 +167,12 @@ int armon_free(armon_ctx *ctx, double *dptr);
 int armon_copy_h2d(armon_ctx *ctx, double *dst_dev, const double *src_host, uint64_t n_elems);
 int armon_copy_d2h(armon_ctx *ctx, double *dst_host, const double *src_dev, uint64_t n_elems);
 int armon_copy_d2d(armon_ctx *ctx, double *dst_dev, const double *src_dev, uint64_t n_elems);
+/* `ArmonParameters{Float32}`: the caller's arrays are Float32, the device arrays (and all arithmetic) stay Float64; the
+ * conversion runs on the device (h2d: exact widening; d2h: round to nearest), through a staging buffer of the context.
+ * A Float32 run therefore carries no Float32 rounding noise of its own: it agrees with the reference's Float64 result
+ * to Float32 precision (tests/test_gpu_parity.py::test_float32_boundary). */
+int armon_copy_h2d_f32(armon_ctx *ctx, double *dst_dev, const float *src_host, uint64_t n_elems);
+int armon_copy_d2h_f32(armon_ctx *ctx, float *dst_host, const double *src_dev, uint64_t n_elems);
 int armon_fill(armon_ctx *ctx, double *dst_dev, double value, uint64_t n_elems);
 /* fills every ghost cell of one array (test/convergence.jl:67-102 poisons ghosts with 1e100) */
 int armon_fill_ghosts(armon_ctx *ctx, armon_dims d, double *arr, double value);

@@ -21,8 +21,8 @@ TESTS = ("Sod", "Sod_y", "Sod_circ", "Bizarrium", "Sedov")
 N = 100
 
 
-def convert(test):
-    path = os.path.join(REF_DIR, f"ref_{test}_64bits.csv")
+def convert(test, bits=64):
+    path = os.path.join(REF_DIR, f"ref_{test}_{bits}bits.csv")
     with open(path) as f:
         header = f.readline().strip()
         dt_str, cycles_str = [s.strip() for s in header.split(",")]
@@ -31,8 +31,10 @@ def convert(test):
     data = np.array([[float(tok) for tok in ln.split(",")] for ln in rows], dtype=np.float64)
     assert data.shape == (N * N, 6)
     fields = {name: data[:, k].reshape(N, N) for k, name in enumerate(("x", "y", "rho", "u", "v", "p"))}
+    if bits == 32:   # "%#16.9e": exact decimal round trip of Float32 values (src/parameters.jl:708-710)
+        fields = {k: v.astype(np.float32) for k, v in fields.items()}
     np.savez_compressed(
-        os.path.join(OUT_DIR, f"ref_{test}_64bits.npz"),
+        os.path.join(OUT_DIR, f"ref_{test}_{bits}bits.npz"),
         dt=np.float64(float(dt_str)), dt_str=np.array(dt_str), cycles=np.int64(int(cycles_str)), **fields)
     print(test, dt_str, cycles_str, {k: float(np.abs(v).max()) for k, v in fields.items()})
 
@@ -41,4 +43,5 @@ if __name__ == "__main__":
     if not os.path.isdir(REF_DIR):
         sys.exit("reference data not found (this script only runs in the build container)")
     for t in TESTS:
-        convert(t)
+        convert(t, 64)
+        convert(t, 32)

@@ -52,7 +52,7 @@ def test_no_cpu_fallback_without_a_device():
 
 
 def test_parameters_reject_what_the_backend_does_not_provide():
-    for kw in (dict(use_gpu=False), dict(device="CUDA"), dict(data_type="Float32"), dict(async_cycle=True),
+    for kw in (dict(use_gpu=False), dict(device="CUDA"), dict(data_type="Float16"), dict(async_cycle=True),
                dict(dt_on_even_cycles=True), dict(nghost=2), dict(cst_dt=True, Dt=0.0), dict(math_mode="sloppy"),
                dict(P=(1, 1, 1))):
         with pytest.raises(armon.SolverException) as e:

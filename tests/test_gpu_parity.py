@@ -481,3 +481,35 @@ def test_compare_is_ref_checkpoint_protocol(tmp_path, capsys):
     diff = [p.name for p in tmp_path.iterdir() if p.name.endswith("_diff")]
     assert len(diff) == 1 and diff[0].startswith("chk_000_cell_update_") and f"Difference file written to {diff[0]}" in out
     other.data.close()
+
+
+@pytest.mark.parametrize("test", GOLDEN_TESTS)
+def test_float32_boundary(test, golden):
+    """`ArmonParameters{Float32}`: the caller's arrays are Float32, the device computes in Float64 (conversion in the
+    host <-> device copies).  Against the reference's golden `ref_*_32bits.csv` (test/reference_data, tolerances
+    reference_functions.jl:56,58: atol 1e-5, rtol 20 eps(Float32)): same cycle count; fields equal to the Float64 golden
+    data rounded to Float32, i.e. as far from the 32-bit golden data as the reference's own two precisions are from each
+    other -- its Float32 arithmetic carries rounding noise above its own tolerance for Sedov and Bizarrium, which a
+    Float64 computation cannot and should not reproduce.  Sod, Sod_y and Sod_circ pass the reference's acceptance test
+    outright."""
+    import os
+    g32 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{test}_32bits.npz"))
+    g64 = golden(test)
+    stats, grid = run_gpu(reference_params(test, data_type="Float32"))
+    assert grid.real("rho").dtype == np.float32
+    assert stats.cycles == int(g32["cycles"]) == int(g64["cycles"])
+    eps32 = float(np.finfo(np.float32).eps)
+    report = {}
+    for var in ("rho", "u", "v", "p"):
+        got = grid.real(var)
+        # our Float32 output is the Float64 result rounded once
+        assert np.array_equal(got, g64[var].astype(np.float32)) or scaled_max_diff(got.astype(np.float64), g64[var]) <= eps32
+        ours = float(np.abs(got.astype(np.float64) - g32[var].astype(np.float64)).max())
+        theirs = float(np.abs(g64[var] - g32[var].astype(np.float64)).max())
+        assert ours <= theirs + 2 * eps32 * float(np.abs(g64[var]).max()), (var, ours, theirs)
+        report[var] = count_differences(got.astype(np.float64), g32[var].astype(np.float64), atol=1e-5, rtol=20 * eps32)
+    assert abs(stats.last_dt - float(g32["dt"])) <= abs(float(g64["dt"]) - float(g32["dt"])) + 1e-13
+    print(f"float32 {test}: cells failing the reference's Float32 acceptance vs ref_{test}_32bits: {report}")
+    if test in ("Sod", "Sod_y", "Sod_circ"):
+        assert sum(report.values()) == 0, report      # the reference's own Float32 acceptance test
+    grid.close()
