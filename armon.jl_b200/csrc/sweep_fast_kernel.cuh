@@ -50,7 +50,7 @@ enum { STG_TMA = 0, STG_CPA16 = 1, STG_CPA8 = 2 };
 struct SweepTmaMaps { CUtensorMap m[4]; };
 
 constexpr int FK_GROUP = 4;                    // rows per staging group (= one TMA box per variable)
-constexpr int FK_NG = 4;                       // groups in the ring: rows a-3 .. a+12 are resident or in flight
+constexpr int FK_NG = 4;                       // groups in the ring: the one being consumed and three in flight
 constexpr int FK_ROWS = FK_GROUP * FK_NG;      // 16 ring rows
 constexpr int FK_VS = FK_GROUP * 32;           // doubles between two variables of the same row
 constexpr int FK_GS = 4 * FK_VS;               // doubles per group
@@ -172,7 +172,7 @@ __device__ __forceinline__ void xeos(const SweepArgs &A, double rho, double ua, 
 //   D  advection flux of interface a-6, E  projection of cell a-7 <- Lagrangian cells a-7, a-6, a-5
 // Each chain commits its results at the end of the step.
 struct PipeF {
-    double cu[4], cp[4], crc[4], cdm[4];                    // cells a-1 .. a-4: ua, p, rho c, rho dx
+    double cu[4], cp[4], crc[4], cdm[4], cut[4], cE[4];     // cells a-1 .. a-4: ua, p, rho c, rho dx, ut, E
     double Gu[4], Gp[4];                                    // Godunov states of interfaces a-1 .. a-3
     double Fu[4], Fp[4], FpFu[4];                           // flux used (GAD or Godunov) of interfaces a-3, a-4, and p u
     double dl[4], dxl[4], Lr[4], Lru[4], Lrt[4], LrE[4];    // Lagrangian cells a-5 .. a-7: dt * flux velocity of the left
@@ -185,7 +185,7 @@ struct PipeF {
 // Per-iteration (4 steps) addressing, hoisted out of the steps: everything a step touches is at a compile-time offset
 // from one of these.
 struct FastIter {
-    const double *gb0, *gb1;     // this lane's column of the ring groups holding rows a-J .. a-J+3 and the 4 rows before
+    const double *gb0;           // this lane's column of the ring group holding rows a-J .. a-J+3
     double *cw;                  // sound-speed ring: slots of the 4 cells of this iteration
     const double *cr;            // ... and of the 4 cells of the previous one
     double *s0, *s3;             // transposed staging tile: slot of the cell emitted at J = 0 (J = 1, 2 follow) / at J = 3
@@ -205,12 +205,12 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     constexpr int CUR = J & 1, PRV = CUR ^ 1;
     const double dx = A.dx;
     const double *row0 = I.gb0 + J * 32;     // row a
-    const double *rowL = I.gb1 + J * 32;     // row a-4
 
     // ---- chain A, cell a: EOS, Godunov state of interface a (cells a-1, a), src/riemann_schemes.jl:21-30 ----
-    double A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp;
+    double A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp, A_ut, A_E;
     {
         const double rho = row0[0], ua = row0[FK_VS], ut = row0[2 * FK_VS], E = row0[3 * FK_VS];
+        A_ut = ut; A_E = E;
         double p, c;
         xeos<EOS>(A, rho, ua, ut, E, p, c);
         I.cw[J * 32] = c;
@@ -253,8 +253,8 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     const double B_FpFu = xmul(B_Fp, B_Fu);
 
     // ---- chain C, Lagrangian cell k = a-4 in conserved form (src/kernels.jl:58-68): its interfaces a-4 (left) and a-3
-    //      (right) were computed two steps / one step ago; ua, dm of the cell are still in slot Z0 of the cell rings
-    //      (chain A commits cell a there at the end of the step), ut and E are re-read from the ring ----
+    //      (right) were computed two steps / one step ago; ua, ut, E, dm of the cell are still in slot Z0 of the cell
+    //      rings (chain A commits cell a there at the end of the step) ----
     double C_dl, C_dxl, C_Lr, C_Lru, C_Lrt, C_LrE;
     {
         C_dl = xmul(dt, P.Fu[Z0]);
@@ -263,8 +263,8 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
         C_Lr = xmul(P.cdm[Z0], rdxl);
         const double kdt = xmul(dt, rdxl);
         C_Lru = xfma(kdt, xsub(P.Fp[Z0], P.Fp[Z3]), xmul(C_Lr, P.cu[Z0]));
-        C_Lrt = xmul(C_Lr, rowL[2 * FK_VS]);
-        C_LrE = xfma(kdt, xsub(P.FpFu[Z0], P.FpFu[Z3]), xmul(C_Lr, rowL[3 * FK_VS]));
+        C_Lrt = xmul(C_Lr, P.cut[Z0]);
+        C_LrE = xfma(kdt, xsub(P.FpFu[Z0], P.FpFu[Z3]), xmul(C_Lr, P.cE[Z0]));
     }
 
     // ---- chain D, advection flux at interface is = a-6 (src/projection_schemes.jl:62-124): upwind cell a-7 (slot Z3,
@@ -333,7 +333,8 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     }
 
     // ---- commit the chains: A -> cell a and interface a (slot Z0), B -> interface a-2 (slot Z2), C -> cell a-4 (slot Z0) ----
-    P.cu[Z0] = A_ua; P.cp[Z0] = A_p; P.crc[Z0] = A_rc; P.cdm[Z0] = A_dm; P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
+    P.cu[Z0] = A_ua; P.cp[Z0] = A_p; P.crc[Z0] = A_rc; P.cdm[Z0] = A_dm; P.cut[Z0] = A_ut; P.cE[Z0] = A_E;
+    P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
     P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
     P.dl[Z0] = C_dl; P.dxl[Z0] = C_dxl; P.Lr[Z0] = C_Lr; P.Lru[Z0] = C_Lru; P.Lrt[Z0] = C_Lrt; P.LrE[Z0] = C_LrE;
 #undef ZS
@@ -531,9 +532,11 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     for (int k = lane; k < FK_CS * 32; k += 32) (&S.cring[0][0])[k] = 1.0;
 
     // ---- staging ----
-    // Group G holds array rows a_begin + 4G .. + 3 in ring slot G & 3.  Iteration `it` consumes group `it`; the oldest
-    // row a step reads is a-4, so group it-1 is dead at the end of iteration `it` and its slot is then refilled with
-    // group it+3: the copies run 8 steps ahead of their use.  Prologue: groups 0, 1, 2.
+    // Group G holds array rows a_begin + 4G .. + 3 in ring slot G & 3.  Iteration `it` consumes group `it` (every value
+    // a later step needs again travels in registers), so its slot is refilled with group it+4 at the end of the
+    // iteration: 12 rows (12 KB per warp, ~14 MB per GPU) are in flight at any time, the copies run 12 steps ahead of
+    // their use -- with 8 the profile showed 6 % of the warp time waiting on the barrier of the next group.
+    // Prologue: groups 0 .. 3.
     const unsigned ring_u32 = fk_smem_u32(&S.ring[0][0][0][0]);
     const unsigned bar_u32 = fk_smem_u32(&S.full[0]);
     const int col0 = (int)(w0 + A.g), row0_arr = (int)(a_begin + A.g);
@@ -600,11 +603,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     issue_group(0);
     issue_group(1);
     issue_group(2);
+    issue_group(3);
 
     PipeF P;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        P.cu[j] = 0.; P.cp[j] = 1.; P.crc[j] = 1.; P.cdm[j] = 1.; P.Gu[j] = 0.; P.Gp[j] = 1.;
+        P.cu[j] = 0.; P.cp[j] = 1.; P.crc[j] = 1.; P.cdm[j] = 1.; P.cut[j] = 0.; P.cE[j] = 1.; P.Gu[j] = 0.; P.Gp[j] = 1.;
         P.Fu[j] = 0.; P.Fp[j] = 1.; P.FpFu[j] = 0.;
         P.dl[j] = 0.; P.dxl[j] = 1.; P.Lr[j] = 1.; P.Lru[j] = 0.; P.Lrt[j] = 0.; P.LrE[j] = 1.;
     }
@@ -617,7 +621,6 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     double *cring = &S.cring[0][lane];
     double *sbase = S.stage + lane * FK_PITCH;
     FastIter I;
-    I.gb1 = ring + (FK_NG - 1) * FK_GS;   // "group -1": benign
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
 #define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS>(A, T, P, I, dt, OK);
@@ -628,13 +631,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         I.cw = cring + p_ * 4 * 32;                                                                         \
         I.cr = cring + (p_ ^ 1) * 4 * 32;                                                                   \
         if (STG == STG_TMA) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
-        else { async_wait<2>(); __syncwarp(); }                                                             \
+        else { async_wait<3>(); __syncwarp(); }                                                             \
     }
 #define FK_END(it)                                                                                          \
     {                                                                                                       \
-        __syncwarp();   /* every lane has read the last row of group it-1: refill its slot */               \
-        issue_group((it) + 3);                                                                              \
-        I.gb1 = I.gb0;                                                                                      \
+        __syncwarp();   /* every lane has read the last row of group it: refill its slot */                 \
+        issue_group((it) + 4);                                                                              \
     }
 
     // warm-up: steps 0 .. 7 fill the head of the dependency cone of the first output, nothing is emitted

@@ -155,15 +155,13 @@ def pin_to_gpu_numa_node(local_rank):
         return 0
 
 
-def oracle_fits_in_host_memory(n, reserve_gb=8.0):
-    """The oracle holds the reference's 16 arrays of (nx+8)(ny+8) doubles; never start one that would push the box
-    into swap / the OOM killer (malloc succeeds under overcommit)."""
-    need = 16 * (n[0] + 8) * (n[1] + 8) * 8
+def host_memory_available():
+    """Bytes of host memory this process may still take (MemAvailable, capped by the container's cgroup limit)."""
     try:
         with open("/proc/meminfo") as f:
             avail = next(int(ln.split()[1]) * 1024 for ln in f if ln.startswith("MemAvailable"))
     except Exception:
-        return True
+        return 1 << 62
     try:   # a container may be capped below what /proc/meminfo shows
         with open("/sys/fs/cgroup/memory.max") as f, open("/sys/fs/cgroup/memory.current") as g:
             cap = f.read().strip()
@@ -171,7 +169,14 @@ def oracle_fits_in_host_memory(n, reserve_gb=8.0):
                 avail = min(avail, int(cap) - int(g.read().strip()))
     except Exception:
         pass
-    return need + reserve_gb * 2**30 < avail
+    return avail
+
+
+def oracle_fits_in_host_memory(n, reserve_gb=8.0):
+    """The oracle holds the reference's 16 arrays of (nx+8)(ny+8) doubles; never start one that would push the box
+    into swap / the OOM killer (malloc succeeds under overcommit)."""
+    need = 16 * (n[0] + 8) * (n[1] + 8) * 8
+    return need + reserve_gb * 2**30 < host_memory_available()
 
 
 # -------------------------------------------------------------------------------------------------------------
@@ -338,12 +343,17 @@ class GpuJob:
         armon, grid, params = self.armon, self.grid, self.params
         names = ("rho", "u", "v", "E")
         armon.init_test(params, grid)          # fresh initial state on the device -> host copy (untimed set-up)
-        pinned = {k: torch.empty(grid.cell_count, dtype=torch.float64, pin_memory=True) for k in names}
+        # One set of host buffers per rank, used in both directions (the result overwrites the input, as a caller that
+        # advances a state in place would do).  Pinned when every rank's set fits comfortably in host memory
+        # (8 ranks x 8.6 GB at 16384^2 per GPU), pageable otherwise -- slower copies, but never a box out of memory.
+        need = 4 * grid.cell_count * 8
+        pin = host_memory_available() > 1.5 * need * self.world + (16 << 30)
         host0 = {}
         for k in names:
-            getattr(grid.device_data, k).copy_to_host(pinned[k].numpy())
-            host0[k] = pinned[k].numpy()
-        out_pinned = {k: torch.empty(grid.cell_count, dtype=torch.float64, pin_memory=True) for k in names}
+            buf = torch.empty(grid.cell_count, dtype=torch.float64, pin_memory=pin)
+            getattr(grid.device_data, k).copy_to_host(buf.numpy())
+            host0[k] = buf.numpy()
+        out_pinned = {k: torch.from_numpy(host0[k]) for k in names}
         self.sync_all()
         t0 = time.perf_counter()
         for k in names:                        # h2d of the job's input
@@ -369,6 +379,7 @@ class GpuJob:
         d2h = (4 * grid.cell_count * 8 + steps * C.sizeof(armon.backend.armon_time_state)) / steps
         return {"value": self.global_cells * steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": steps,
+                "host_buffers": "pinned" if pin else "pageable (not enough host memory to pin every rank's buffers)",
                 "note": "h2d of rho,u,v,E from pinned host memory + K x (solver_cycle + blocking read of the time-step "
                         "state) + finalize + d2h of rho,u,v,E, wall clock, max over ranks; the two field transfers are "
                         "one-off per job (a real run to maxtime is thousands of cycles)"}
