@@ -172,6 +172,7 @@ struct BcFillArgs {
     double *rho, *ua, *ut, *E;
     long long nm, nw, pitch;
     int g, lo, hi;
+    int tiled;              // band-tiled layout (common.cuh): the ghost rows of a side are one band
     double fa_lo, ft_lo, fa_hi, ft_hi;
 };
 
@@ -181,7 +182,8 @@ __global__ void k_bc_fill(BcFillArgs B)
     const int k = blockIdx.y, side = blockIdx.z;
     if (w >= B.nw || !(side == 0 ? B.lo : B.hi)) return;
     const long long src_row = side == 0 ? k : B.nm - 1 - k, dst_row = side == 0 ? -1 - k : B.nm + k;
-    const long long is = (src_row + B.g) * B.pitch + w + B.g, id = (dst_row + B.g) * B.pitch + w + B.g;
+    const long long is = layout_index(B.tiled != 0, src_row + B.g, w + B.g, B.pitch);
+    const long long id = layout_index(B.tiled != 0, dst_row + B.g, w + B.g, B.pitch);
     const double fa = side == 0 ? B.fa_lo : B.fa_hi, ft = side == 0 ? B.ft_lo : B.ft_hi;
     B.rho[id] = B.rho[is];
     B.E[id] = B.E[is];
@@ -192,8 +194,10 @@ __global__ void k_bc_fill(BcFillArgs B)
 // ---- layout helpers ---------------------------------------------------------------------------------------------
 struct Ptr4 { const double *in[4]; double *out[4]; };
 
-// out[c][r] = in[r][c] for 4 arrays at once; rows x cols are the full array extents including ghosts
-__global__ void k_transpose4(Ptr4 P, long long rows, long long cols)
+// Change of layout of 4 arrays at once: out[c][r] = in[r][c] (transpose) or out[r][c] = in[r][c], each side row-major
+// or band-tiled (common.cuh); rows x cols are the full extents of the INPUT including ghosts.  Runs where the state
+// enters or leaves the marching layouts (first sweep, finalize, an unpredicted change of axis), never inside the loop.
+__global__ void k_relayout4(Ptr4 P, long long rows, long long cols, int in_tiled, int out_tiled, int transpose)
 {
     __shared__ double tile[4][32][33];
     const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
@@ -202,14 +206,19 @@ __global__ void k_transpose4(Ptr4 P, long long rows, long long cols)
     for (int k = 0; k < 4; k++)
         for (int j = ty; j < 32; j += 8) {
             const long long r = r0 + j, c = c0 + tx;
-            if (r < rows && c < cols) tile[k][j][tx] = P.in[k][r * cols + c];
+            if (r < rows && c < cols) tile[k][j][tx] = P.in[k][layout_index(in_tiled != 0, r, c, cols)];
         }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; k++)
         for (int j = ty; j < 32; j += 8) {
-            const long long c = c0 + j, r = r0 + tx;
-            if (r < rows && c < cols) P.out[k][c * rows + r] = tile[k][tx][j];
+            if (transpose) {
+                const long long c = c0 + j, r = r0 + tx;
+                if (r < rows && c < cols) P.out[k][layout_index(out_tiled != 0, c, r, rows)] = tile[k][tx][j];
+            } else {
+                const long long r = r0 + j, c = c0 + tx;
+                if (r < rows && c < cols) P.out[k][layout_index(out_tiled != 0, r, c, cols)] = tile[k][j][tx];
+            }
         }
 }
 
@@ -219,7 +228,7 @@ __global__ void k_transpose4(Ptr4 P, long long rows, long long cols)
 //   end yet: the other buffer set still holds the input of the last real sweep); mode 2 (finalize): unless cycles were
 //   enqueued past the end (then mode 1 already saved them before its source was overwritten).
 template <int EOS>
-__global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, const double *rho, const double *u,
+__global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, int in_tiled, const double *rho, const double *u,
                           const double *v, const double *E, double gamma, double *p, double *c, double *gg,
                           const DeviceTimeState *ts, int mode)
 {
@@ -228,7 +237,8 @@ __global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, 
     for (long long iy = blockIdx.y; iy < ny; iy += gridDim.y)
         for (long long ix = (long long)blockIdx.x * blockDim.x + threadIdx.x; ix < nx; ix += (long long)gridDim.x * blockDim.x) {
             const long long io = (iy + g) * (nx + 2 * g) + (ix + g);
-            const long long ii = in_transposed ? (ix + g) * (ny + 2 * g) + (iy + g) : io;
+            const long long ii = in_transposed ? layout_index(in_tiled != 0, ix + g, iy + g, ny + 2 * g)
+                                               : layout_index(in_tiled != 0, iy + g, ix + g, nx + 2 * g);
             sd pp, cc, g_;
             RangeFlag f;
             if (EOS == ARMON_EOS_BIZARRIUM) {
@@ -246,14 +256,14 @@ __global__ void k_eos_pcg(long long nx, long long ny, int g, int in_transposed, 
 // ---- per-cycle diagnostics (conservation_vars, src/reductions.jl:202-298) on the current buffers ---------------
 // Fixed summation tree: every array row of the current layout is summed by one CTA (strided per-thread partial sums,
 // then a binary tree), the row partials by one CTA in the same way: deterministic for a given grid and layout.
-__global__ void k_diag_rows(long long n_rows, long long n_cols, long long pitch, int g, const double *rho,
+__global__ void k_diag_rows(long long n_rows, long long n_cols, long long pitch, int g, int tiled, const double *rho,
                             const double *E, double *row_m, double *row_e)
 {
     __shared__ double sm[TPB], se[TPB];
     for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
         double m = 0.0, e = 0.0;
         for (long long c = threadIdx.x; c < n_cols; c += TPB) {
-            const long long i = (r + g) * pitch + (c + g);
+            const long long i = layout_index(tiled != 0, r + g, c + g, pitch);
             m = __dadd_rn(m, rho[i]);
             e = __dadd_rn(e, __dmul_rn(rho[i], E[i]));
         }
@@ -337,6 +347,10 @@ struct armon_solver {
     bool              cur_transposed = false;  // false: canonical rows = y; true: rows = x
     bool              have_prev = false;       // the other set still holds the state at the start of the last sweep
     bool              prev_transposed = false;
+    // band-tiled marching layout (sweep_fast_kernel.cuh, 5.): `tiled_ok` = this block can run it (fast mode, TMA staging,
+    // extents multiples of 8); whether it is used is decided per group and across ranks (decide_tiling)
+    bool              tiled_ok = false, cur_tiled = false, prev_tiled = false;
+    sweep_fast_fn_t   fast_tiled_kernel[2] = {nullptr, nullptr}, fast_tiled_cons_kernel[2] = {nullptr, nullptr};
     DeviceTimeState  *own_ts = nullptr;        // the time-step state of the solver's private group
     DeviceTimeState  *ts = nullptr;            // the state in use: own_ts, or the one of the block group it belongs to
     armon_group      *self = nullptr;          // private group of one
@@ -362,7 +376,7 @@ struct armon_solver {
     long long         diag_base = 0, diag_cap = 0;
     double           *cons_m = nullptr, *cons_e = nullptr;   // set by group_sweep for the last sweep of a cycle
     bool              cons_done = false;
-    std::map<std::tuple<const double *, long long, long long>, CUtensorMap> tmaps;   // (array, rows, pitch) -> tensor map
+    std::map<std::tuple<const double *, long long, long long, int>, CUtensorMap> tmaps;   // (array, rows, pitch, box rows) -> tensor map
     bool              overlap = true;          // interior / edge split of a sweep around the halo exchange (ARMON_B200_OVERLAP=0 disables)
     unsigned         *fix_count = nullptr;     // two counters, used alternately by successive sweeps
     unsigned long long *fix_list = nullptr;
@@ -386,6 +400,8 @@ struct armon_group {
     cudaEvent_t                ev_dt[2] = {nullptr, nullptr};    // all-reduce of accumulator slot 0 / 1 done
     bool                       last_axis_is_x[2] = {true, true}; // axis of the sweep that filled accumulator slot 0 / 1
     bool                       timed = false;
+    int                        tiled = -1;              // band-tiled layout between the sweeps: -1 undecided, 0 no, 1 yes
+    int                       *agree = nullptr;         // device word of the cross-rank agreement on `tiled`
     // CUDA graph of two consecutive cycles (one period of the buffer rotation, the accumulator slots and the
     // alternating splittings)
     int                        graph_mode = 0;          // 0 auto, 1 on, 2 off (armon_solver_desc.cuda_graph)
@@ -432,29 +448,29 @@ void drop_graph(armon_group *G)
     }
 }
 
-// Transpose the current state into the other buffer set.
-int transpose_current(armon_solver *s)
+// Rewrite the current state into the other buffer set in another layout (orientation x row-major / band-tiled).
+int relayout_current(armon_solver *s, bool transposed, bool tiled)
 {
+    if (transposed == s->cur_transposed && tiled == s->cur_tiled) return ARMON_OK;
     const armon_dims &D = s->d.dims;
     const long long rows = s->cur_transposed ? D.nx + 2 * D.g : D.ny + 2 * D.g;
     const long long cols = s->cur_transposed ? D.ny + 2 * D.g : D.nx + 2 * D.g;
     Ptr4 P;
     for (int k = 0; k < 4; k++) { P.in[k] = s->buf[s->cur][k]; P.out[k] = s->buf[1 - s->cur][k]; }
     const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), 1), block(32, 8, 1);
-    k_transpose4<<<grid, block, 0, s->ctx->stream>>>(P, rows, cols);
+    k_relayout4<<<grid, block, 0, s->ctx->stream>>>(P, rows, cols, s->cur_tiled, tiled, transposed != s->cur_transposed);
     ARMON_LAUNCH_CHECK(s->ctx);
     s->cur = 1 - s->cur;
-    s->cur_transposed = !s->cur_transposed;
+    s->cur_transposed = transposed;
+    s->cur_tiled = tiled;
     s->have_prev = false;
     return ARMON_OK;
 }
 
-// A sweep along `axis` marches along the strided dimension: X needs the transposed layout, Y the canonical one.
-int ensure_layout(armon_solver *s, int axis)
+// A sweep along `axis` marches along the strided dimension: X needs the transposed orientation, Y the canonical one.
+int ensure_layout(armon_solver *s, int axis, bool tiled)
 {
-    const bool need_transposed = (axis == ARMON_AXIS_X);
-    if (need_transposed != s->cur_transposed) return transpose_current(s);
-    return ARMON_OK;
+    return relayout_current(s, axis == ARMON_AXIS_X, tiled);
 }
 
 // block_ghost_exchange with RemoteTaskBlocks (src/halo_exchange.jl:286-354): the two sides along `axis`.  In the
@@ -541,9 +557,28 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         int seg = (s->d.march_segment + 15) / 16 * 16;
         return seg;
     }
+    if (s->use_fast) {
+        // Fast kernels (8 warps = 2 CTAs per SM): every CTA marches seg + 12 rows (the warm-up rows of a segment are
+        // redundant work) and the CTAs run in waves of 2 x SMs, so the sweep costs about waves x (seg + 12) row times.
+        // Take the multiple of 16 that minimises it -- a power of two can sit just above a whole number of waves (the
+        // tiled layout has one more, mostly empty, column of CTAs: 65 x 32 CTAs at 8192^2 are 7.03 waves).
+        const long long g = s->tiled_ok ? s->d.dims.g : 0;
+        const long long ncol = (nw + g + ASYNC_TPB - 1) / ASYNC_TPB;
+        const long long slots = 2LL * s->ctx->sm_count;
+        long long best_cost = -1;
+        int best = 16;
+        for (int seg = 16; seg <= 4096; seg += 16) {
+            const long long nseg = (nm + seg - 1) / seg;
+            const long long waves = (ncol * nseg + slots - 1) / slots;
+            const long long cost = waves * (seg + 12);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = seg; }   // ties: the longer segment
+            if (seg >= nm) break;
+        }
+        return best;
+    }
     // as long as possible (the warm-up rows of every segment are redundant work) while keeping >= 6 waves of CTAs; the
     // staged kernels run 8 warps per SM whatever their CTA size
-    const bool staged_ok = s->use_fast || (s->use_staged && ((nw + 2 * s->d.dims.g) % 2) == 0);
+    const bool staged_ok = s->use_staged && ((nw + 2 * s->d.dims.g) % 2) == 0;
     const long long cols_per_cta = staged_ok ? ASYNC_TPB : SWEEP_TPB;
     const long long ctas_per_sm = staged_ok ? 256 / ASYNC_TPB : 2;
     const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
@@ -557,15 +592,17 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
 }
 
 // Tensor map of one input array in the marching layout: a 2-D Float64 tensor [rows][pitch], box = 4 rows x 32 columns
-// (one staging group of one warp, sweep_fast_kernel.cuh).  cuTensorMapEncodeTiled is reached through the runtime's
+// (one staging group of one warp, sweep_fast_kernel.cuh); band-tiled arrays are described as [bands][4 pitch] with a box
+// of 1 band x 128 elements (the 4 adjacent tiles of the same 4 rows x 32 columns).  cuTensorMapEncodeTiled is reached through the runtime's
 // driver entry point table, so the library does not link against libcuda.  Maps are cached per (array, extent).
 typedef CUresult (*encode_tiled_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int tensor_map_for(armon_solver *s, const double *arr, long long rows, long long pitch, CUtensorMap *out)
+int tensor_map_for(armon_solver *s, const double *arr, long long rows, long long pitch, int box_rows, int box_cols,
+                   CUtensorMap *out)
 {
-    const auto key = std::make_tuple(arr, rows, pitch);
+    const auto key = std::make_tuple(arr, rows, pitch, box_rows);
     const auto it = s->tmaps.find(key);
     if (it != s->tmaps.end()) { *out = it->second; return ARMON_OK; }
     static encode_tiled_fn_t encode = nullptr;
@@ -582,7 +619,7 @@ int tensor_map_for(armon_solver *s, const double *arr, long long rows, long long
     alignas(64) CUtensorMap map;
     const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(double)};   // bytes, multiple of 16: even pitch
-    const cuuint32_t box[2] = {32u, (cuuint32_t)FK_GROUP};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(arr), dims, strides, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -656,16 +693,26 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     }
 
     const bool fast_launch = s->use_fast;
-    const int stg = (A.pitch_in % 2) == 0 ? s->fast_stg : STG_CPA8;
+    const bool tiled = s->cur_tiled;   // layout of the input and of the output (ensure_layout ran before)
+    if (tiled && !(fast_launch && s->tiled_ok)) {
+        armon_set_error("internal: band-tiled state without the tiled kernels");
+        return ARMON_ERR_INVALID;
+    }
+    const int stg = tiled ? STG_TMA : (A.pitch_in % 2) == 0 ? s->fast_stg : STG_CPA8;
     SweepTmaMaps maps;
     if (fast_launch && stg == STG_TMA) {
-        for (int k = 0; k < 4; k++)
-            if (int rc = tensor_map_for(s, A.in[k], A.nm + 2 * D.g, A.pitch_in, &maps.m[k])) return rc;
+        for (int k = 0; k < 4; k++) {
+            const int rc = tiled ? tensor_map_for(s, A.in[k], (A.nm + 2 * D.g) / FK_GROUP, FK_GROUP * A.pitch_in, 1, FK_GROUP * 32, &maps.m[k])
+                                 : tensor_map_for(s, A.in[k], A.nm + 2 * D.g, A.pitch_in, FK_GROUP, 32, &maps.m[k]);
+            if (rc) return rc;
+        }
     } else {
         memset(&maps, 0, sizeof(maps));
     }
+    const int tr = A.transpose_out ? 1 : 0;
     // per-cycle diagnostics: the last sweep of the cycle accumulates the conservation sums itself when it can
-    const bool cons = fast_launch && stg == STG_TMA && s->cons_m != nullptr && s->fast_cons_kernel[A.transpose_out ? 1 : 0];
+    const bool cons = fast_launch && stg == STG_TMA && s->cons_m != nullptr &&
+                      (tiled ? s->fast_tiled_cons_kernel[tr] : s->fast_cons_kernel[tr]) != nullptr;
     A.cons_m = cons ? s->cons_m : nullptr;
     A.cons_e = cons ? s->cons_e : nullptr;
     s->cons_done = cons;
@@ -698,9 +745,11 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     auto launch = [&](long long y_base, long long y_jump, long long ny, cudaStream_t st) -> int {
         A.y_base = (int)y_base;
         A.y_jump = (int)y_jump;
-        const dim3 grid((unsigned)((A.nw + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
+        // (tiled: the threads are shifted by the g ghost columns, sweep_fast_kernel.cuh 5.)
+        const dim3 grid((unsigned)((A.nw + (tiled ? D.g : 0) + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
         if (fast_launch)
-            (cons ? s->fast_cons_kernel[A.transpose_out ? 1 : 0] : s->fast_kernel[stg][A.transpose_out ? 1 : 0])
+            (tiled ? (cons ? s->fast_tiled_cons_kernel[tr] : s->fast_tiled_kernel[tr])
+                   : (cons ? s->fast_cons_kernel[tr] : s->fast_kernel[stg][tr]))
                 <<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
         else if (staged_launch)
             s->staged_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->staged_smem, st>>>(A);
@@ -715,6 +764,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         B.rho = const_cast<double *>(A.in[0]); B.ua = const_cast<double *>(A.in[1]);
         B.ut = const_cast<double *>(A.in[2]); B.E = const_cast<double *>(A.in[3]);
         B.nm = A.nm; B.nw = A.nw; B.pitch = A.pitch_in; B.g = A.g; B.lo = A.mirror_lo; B.hi = A.mirror_hi;
+        B.tiled = tiled ? 1 : 0;
         B.fa_lo = A.bc_a_lo; B.ft_lo = A.bc_t_lo; B.fa_hi = A.bc_a_hi; B.ft_hi = A.bc_t_hi;
         const dim3 bgrid((unsigned)((A.nw + TPB - 1) / TPB), (unsigned)A.g, 2);
         k_bc_fill<<<bgrid, TPB, 0, st>>>(B);
@@ -751,6 +801,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
 
     s->have_prev = true;
     s->prev_transposed = s->cur_transposed;
+    s->prev_tiled = s->cur_tiled;
     s->cur = out_set;
     if (A.transpose_out) s->cur_transposed = !s->cur_transposed;
     return ARMON_OK;
@@ -761,7 +812,7 @@ int group_sweep(armon_group *G, int axis, double dt_factor, int acc_slot, int ne
 {
     NvtxRange r(axis == ARMON_AXIS_X ? "X" : "Y");
     for (armon_solver *b : G->blocks) {
-        if (int rc = ensure_layout(b, axis)) return rc;
+        if (int rc = ensure_layout(b, axis, G->tiled == 1)) return rc;
         const bool diag = last_of_cycle && G->diag_ring != nullptr;
         b->cons_m = diag ? G->diag_rows + b->diag_base : nullptr;
         b->cons_e = diag ? G->diag_rows + G->diag_rows_cap + b->diag_base : nullptr;
@@ -848,11 +899,11 @@ int launch_eos_pcg(armon_solver *s, int mode)
     const dim3 grid((unsigned)(gx < 64 ? gx : 64), (unsigned)(D.ny < 64 ? D.ny : 64), 1);
     if (s->d.tc.eos == ARMON_EOS_BIZARRIUM)
         k_eos_pcg<ARMON_EOS_BIZARRIUM><<<grid, TPB, 0, s->ctx->stream>>>(
-            D.nx, D.ny, (int)D.g, s->prev_transposed, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1],
+            D.nx, D.ny, (int)D.g, s->prev_transposed, s->prev_tiled, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1],
             s->pcg[2], s->ts, mode);
     else
         k_eos_pcg<ARMON_EOS_PERFECT_GAS><<<grid, TPB, 0, s->ctx->stream>>>(
-            D.nx, D.ny, (int)D.g, s->prev_transposed, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1],
+            D.nx, D.ny, (int)D.g, s->prev_transposed, s->prev_tiled, b[0], b[1], b[2], b[3], s->d.tc.gamma, s->pcg[0], s->pcg[1],
             s->pcg[2], s->ts, mode);
     ARMON_LAUNCH_CHECK(s->ctx);
     return ARMON_OK;
@@ -869,7 +920,7 @@ int launch_diagnostics(armon_group *G)
         const armon_dims &D = b->d.dims;
         const long long n_rows = b->cur_transposed ? D.nx : D.ny, n_cols = b->cur_transposed ? D.ny : D.nx;
         const unsigned nblk = (unsigned)(n_rows < 4096 ? n_rows : 4096);
-        k_diag_rows<<<nblk, TPB, 0, G->ctx->stream>>>(n_rows, n_cols, n_cols + 2 * D.g, (int)D.g, b->buf[b->cur][0],
+        k_diag_rows<<<nblk, TPB, 0, G->ctx->stream>>>(n_rows, n_cols, n_cols + 2 * D.g, (int)D.g, b->cur_tiled, b->buf[b->cur][0],
                                                       b->buf[b->cur][3], row_m + b->diag_base, row_e + b->diag_base);
         ARMON_LAUNCH_CHECK(G->ctx);
     }
@@ -880,11 +931,33 @@ int launch_diagnostics(armon_group *G)
     return ARMON_OK;
 }
 
+// Band-tiled layout between the sweeps (sweep_fast_kernel.cuh, 5.): used when every block of the group can run it and,
+// since the ghost rows travel between ranks as raw 4-row bands, when every rank of the communicator says the same
+// (one all-reduce at the first cycle of the group's first run; every rank enqueues the same sequence of calls).
+int decide_tiling(armon_group *G)
+{
+    if (G->tiled >= 0) return ARMON_OK;
+    int ok = 1;
+    for (const armon_solver *b : G->blocks) ok = ok && b->tiled_ok;
+    if (multi_rank(G)) {
+        if (!G->agree) ARMON_CUDA(cudaMalloc(&G->agree, sizeof(int)));
+        cudaStream_t cs = G->ctx->comm_stream;
+        ARMON_CUDA(cudaMemcpyAsync(G->agree, &ok, sizeof(int), cudaMemcpyHostToDevice, cs));
+        ARMON_NCCL(ncclAllReduce(G->agree, G->agree, 1, ncclInt, ncclMin, G->ctx->comm, cs));
+        ARMON_CUDA(cudaMemcpyAsync(&ok, G->agree, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        ARMON_CUDA(cudaStreamSynchronize(cs));
+    }
+    G->tiled = ok ? 1 : 0;
+    if (getenv("ARMON_B200_VERBOSE")) fprintf(stderr, "[armon_b200] band-tiled layout: %s\n", G->tiled ? "on" : "off");
+    return ARMON_OK;
+}
+
 int enqueue_cycle(armon_group *G)
 {
     NvtxRange r("solver_cycle");
     const armon_solver_desc &d = G->blocks[0]->d;
     if (!G->started) {
+        if (int rc = decide_tiling(G)) return rc;
         // cycle 0: EOS_init + first time step (src/solver.jl:291-297); its maxima go to slot 1 ("cycle -1")
         NvtxRange r2("time_step");
         for (armon_solver *b : G->blocks)
@@ -1013,6 +1086,7 @@ int group_reset(armon_group *G)
     for (armon_solver *b : G->blocks) {
         b->cur = 0;
         b->cur_transposed = false;
+        b->cur_tiled = false;
         b->have_prev = false;
     }
     return ARMON_OK;
@@ -1080,9 +1154,7 @@ int solver_finalize(armon_solver *s)
     if (int rc = launch_eos_pcg(s, 2)) return rc;
     s->have_prev = false;
     // 2. canonical layout, in main_vars
-    if (s->cur_transposed) {
-        if (int rc = transpose_current(s)) return rc;
-    }
+    if (int rc = relayout_current(s, false, false)) return rc;
     if (s->cur != 0) {
         for (int k = 0; k < 4; k++)
             ARMON_CUDA(cudaMemcpyAsync(s->buf[0][k], s->buf[1][k], (size_t)n_elems(s) * sizeof(double),
@@ -1128,7 +1200,7 @@ int group_diagnostics(armon_group *G, int32_t capacity)
         for (int axis = 0; axis < 2; axis++) {
             const long long nm = axis == ARMON_AXIS_X ? D.nx : D.ny, nw = axis == ARMON_AXIS_X ? D.ny : D.nx;
             const long long seg = pick_segment(b, nm, nw);
-            const long long parts = ((nm + seg - 1) / seg) * ((nw + ASYNC_TPB - 1) / ASYNC_TPB) * (ASYNC_TPB / 32);
+            const long long parts = ((nm + seg - 1) / seg) * ((nw + D.g + ASYNC_TPB - 1) / ASYNC_TPB) * (ASYNC_TPB / 32);
             cap = parts > cap ? parts : cap;
         }
         b->diag_base = rows;
@@ -1182,6 +1254,7 @@ void group_free_common(armon_group *G)
     if (G->diag_ring) cudaFree(G->diag_ring);
     if (G->diag_head) cudaFree(G->diag_head);
     if (G->diag_rows) cudaFree(G->diag_rows);
+    if (G->agree) cudaFree(G->agree);
 }
 
 // Select the marching kernels of a solver from its descriptor.
@@ -1241,16 +1314,28 @@ int select_kernels(armon_solver *s)
                 }
             }
         s->use_fast = ok;
+        // band-tiled layout: extents multiples of 8 (whole tiles and bands in both orientations), TMA staging;
+        // ARMON_B200_TILED=0 keeps the row-major layouts (comparison runs, tests)
+        const char *tl = getenv("ARMON_B200_TILED");
+        bool tiled = ok && s->fast_stg == STG_TMA && D.nx % 8 == 0 && D.ny % 8 == 0 && !(tl && atoi(tl) == 0);
         for (int tr = 0; tr < 2 && ok; tr++) {
-            sweep_fast_fn_t fn = biz ? sweep_fast_table_tma_cons_biz(rl, desc->projection, tr)
-                                     : sweep_fast_table_tma_cons_pg(rl, desc->projection, tr);
-            s->fast_cons_kernel[tr] = fn;
-            if (!fn) continue;
-            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(ASYNC_TPB / 32 * sizeof(FastWarpShared))));
-            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                            cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+            sweep_fast_fn_t fns[3];
+            fns[0] = biz ? sweep_fast_table_tma_cons_biz(rl, desc->projection, tr) : sweep_fast_table_tma_cons_pg(rl, desc->projection, tr);
+            fns[1] = biz ? sweep_fast_table_tiled_biz(rl, desc->projection, tr) : sweep_fast_table_tiled_pg(rl, desc->projection, tr);
+            fns[2] = biz ? sweep_fast_table_tiled_cons_biz(rl, desc->projection, tr) : sweep_fast_table_tiled_cons_pg(rl, desc->projection, tr);
+            s->fast_cons_kernel[tr] = fns[0];
+            s->fast_tiled_kernel[tr] = fns[1];
+            s->fast_tiled_cons_kernel[tr] = fns[2];
+            tiled = tiled && fns[1] != nullptr;
+            for (sweep_fast_fn_t fn : fns) {
+                if (!fn) continue;
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(ASYNC_TPB / 32 * sizeof(FastWarpShared))));
+                ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+            }
         }
+        s->tiled_ok = tiled;
     }
     if (variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT) {
         bool ok = true;
@@ -1392,6 +1477,7 @@ int armon_solver_bind(armon_solver *s, double *const main_vars[4], double *const
     s->bound = true;
     s->cur = 0;
     s->cur_transposed = false;
+    s->cur_tiled = false;
     s->have_prev = false;
     s->tmaps.clear();
     drop_graph(s->group);
@@ -1448,7 +1534,7 @@ int armon_solver_halo_exchange(armon_solver *s, int axis)
 {
     if (int rc = solver_check(s)) return rc;
     ARMON_CHECK_ARG(axis == ARMON_AXIS_X || axis == ARMON_AXIS_Y, "axis");
-    if (int rc = ensure_layout(s, axis)) return rc;
+    if (int rc = ensure_layout(s, axis, false)) return rc;
     if (int rc = comm_begin(s)) return rc;
     if (int rc = halo_exchange(s, axis, s->ctx->comm_stream)) return rc;
     return comm_end(s, true);

@@ -83,17 +83,22 @@ sweep_fast_fn_t sweep_fast_table_cpa8_biz(int rl, int proj, int tr);
 // TMA staging + conservation sums (the last sweep of a cycle when the per-cycle diagnostics are on)
 sweep_fast_fn_t sweep_fast_table_tma_cons_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_tma_cons_biz(int rl, int proj, int tr);
+// band-tiled layout between the sweeps (LAY_TILED), TMA staging, without / with the conservation sums
+sweep_fast_fn_t sweep_fast_table_tiled_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_tiled_biz(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_tiled_cons_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_tiled_cons_biz(int rl, int proj, int tr);
 
-#define ARMON_FAST_ROW(STG, RLV, EOS, CONS)                                                  \
-    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS>}, \
-     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS>}}
+#define ARMON_FAST_ROW(STG, RLV, EOS, CONS, LAY)                                             \
+    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS, LAY>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS, LAY>}, \
+     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS, LAY>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS, LAY>}}
 
-#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS)                                        \
+#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS, LAY)                                   \
     sweep_fast_fn_t NAME(int rl, int proj, int tr)                                          \
     {                                                                                       \
         static const sweep_fast_fn_t table[4][2][2] = {                                     \
-            ARMON_FAST_ROW(STG, 0, EOS, CONS), ARMON_FAST_ROW(STG, 1, EOS, CONS),           \
-            ARMON_FAST_ROW(STG, 2, EOS, CONS), ARMON_FAST_ROW(STG, 3, EOS, CONS),           \
+            ARMON_FAST_ROW(STG, 0, EOS, CONS, LAY), ARMON_FAST_ROW(STG, 1, EOS, CONS, LAY), \
+            ARMON_FAST_ROW(STG, 2, EOS, CONS, LAY), ARMON_FAST_ROW(STG, 3, EOS, CONS, LAY), \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \

@@ -38,6 +38,18 @@
 //    of this kernel therefore start 4 cells early: segment k covers cells [k seg - 4, (k+1) seg - 4) (the first one
 //    starts with 4 masked virtual cells, the last one runs to the end of the domain), and every full chunk is one
 //    aligned 64-byte unit per output row whenever the output pitch is a multiple of 8.
+//
+// 5. BAND-TILED LAYOUT BETWEEN SWEEPS (LAY_TILED; grids whose extents are multiples of 8).  With row-major arrays the
+//    transposed output of 4. leaves a warp as isolated 64-byte pieces 128 KB apart; measured on the Godunov sweep
+//    (memory-bound), that store pattern caps a transposing sweep at 0.77 of the copy bandwidth whatever the arithmetic
+//    (pieces of 128 B: 0.79, 256 B: 0.865, 512 B: 0.87, 2 KB: 0.89 -- profiles/README.md).  In the tiled layout
+//    (common.cuh, tiled_index: bands of 4 rows, tiles of [4 rows][8 columns]) the same flush writes the 4 rows of a band
+//    as one contiguous 256-byte tile, and the next sweep fetches a [4 rows x 32 columns] staging group as one contiguous
+//    1 KB run (4 adjacent tiles) instead of 4 row pieces.  Threads are shifted by 4 columns (lane 0 of a warp <-> array
+//    column 32 k, i.e. cell 32 k - 4) so that a warp's columns are whole tiles on the input side and whole bands on the
+//    output side; the 4 ghost columns this brings into the first warp are masked like the ragged tail.  The arithmetic
+//    is untouched: results are bit-identical to the row-major path.  The ghost rows of a side are exactly one band, so
+//    the boundary-condition fill only changes its indexing and the halo copies (NCCL, local blocks) do not change at all.
 #pragma once
 
 #include <cuda.h>
@@ -45,8 +57,10 @@
 #include "sweep_async_kernel.cuh"
 
 enum { STG_TMA = 0, STG_CPA16 = 1, STG_CPA8 = 2 };
+enum { LAY_ROWS = 0, LAY_TILED = 1 };          // layout of the input AND of the output of a sweep
 
-// the four input arrays of a sweep (rho, ua, ut, E) as 2-D tensors [array rows][pitch], box = 4 rows x 32 columns
+// the four input arrays of a sweep (rho, ua, ut, E) as 2-D tensors: LAY_ROWS [array rows][pitch], box = 4 rows x 32
+// columns; LAY_TILED [bands][4 pitch], box = 1 band x 128 elements (4 adjacent tiles = the same 4 rows x 32 columns)
 struct SweepTmaMaps { CUtensorMap m[4]; };
 
 constexpr int FK_GROUP = 4;                    // rows per staging group (= one TMA box per variable)
@@ -180,6 +194,7 @@ struct PipeF {
     double T[2][4];                                         // T+ of the cell pairs (a-6, a-5) / (a-7, a-6)
     double S[2][4];                                         // s' of cells a-6 / a-7
     double Adv[2][4];                                       // advection fluxes of interfaces a-6 / a-7
+    double Q[4][4];                                         // tiled transposed output: the 4 cells of a 32-byte unit, per variable
 };
 
 // Per-iteration (4 steps) addressing, hoisted out of the steps: everything a step touches is at a compile-time offset
@@ -191,12 +206,16 @@ struct FastIter {
     double *s0, *s3;             // transposed staging tile: slot of the cell emitted at J = 0 (J = 1, 2 follow) / at J = 3
     long long o_it;              // direct stores: element offset of the cell emitted at J = 0
     int rem;                     // cells of the segment still to emit, counting the one of J = 0 (<= 0: none)
+    long long q_off;             // tiled transposed stores: element offset of the 4-cell unit completed at J = 2
+    bool qok;                    // ... and whether it is stored (real column, unit inside the segment)
 };
+
+__device__ __forceinline__ void fk_store4(double *p, double a, double b, double c, double d);
 
 // One march step at cell a; J = (a - a_begin) & 3 static.  EMIT / TR compile-time as in march_compute2; `ok`: the
 // thread's column holds a real cell (false also for the steps that run the emitting code on cells before the segment,
 // see the kernel).
-template <int RL, int PROJ, int EOS, int J, int TR, int EMIT, int CONS>
+template <int RL, int PROJ, int EOS, int J, int TR, int EMIT, int CONS, int LAY>
 __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, PipeF &P, const FastIter &I,
                                           const double dt, const bool ok)
 {
@@ -204,7 +223,8 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     constexpr int Z0 = ZS(0), Z1 = ZS(1), Z2 = ZS(2), Z3 = ZS(3);   // also the slots of a-4, a-5, a-6, a-7
     constexpr int CUR = J & 1, PRV = CUR ^ 1;
     const double dx = A.dx;
-    const double *row0 = I.gb0 + J * 32;     // row a
+    // row a of this lane's column: ring group = [variable][row][32 lanes], or [variable][tile][row][8 lanes] (tiled)
+    const double *row0 = I.gb0 + J * (LAY == LAY_TILED ? 8 : 32);
 
     // ---- chain A, cell a: EOS, Godunov state of interface a (cells a-1, a), src/riemann_schemes.jl:21-30 ----
     double A_ua, A_p, A_rc, A_dm, A_Gu, A_Gp, A_ut, A_E;
@@ -317,14 +337,26 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
             T.cm = xadd(T.cm, o_r);
             T.ce = xfma(o_r, o_E, T.ce);
         }
-        if (TR == 1) {
+        if (TR == 1 && LAY == LAY_TILED) {
+            // Transposed output in the tiled layout: the lane's output row holds the march cells of a tile 8 by 8, so 4
+            // consecutive cells of a thread are one aligned 32-byte unit.  They are collected in registers (the unit is
+            // {J = 3 of the previous iteration, J = 0, 1, 2}: segments start on a multiple of 4) and leave as one 256-bit
+            // store per variable: no shared-memory staging, no flush phase that stalls the warp every 8 steps.
+            constexpr int SL = (J + 1) & 3;
+            P.Q[0][SL] = o_r; P.Q[1][SL] = o_ua; P.Q[2][SL] = o_ut; P.Q[3][SL] = o_E;
+            if (J == 2 && I.qok) {
+#pragma unroll
+                for (int v = 0; v < 4; v++) fk_store4(A.out[v] + I.q_off, P.Q[v][0], P.Q[v][1], P.Q[v][2], P.Q[v][3]);
+            }
+        } else if (TR == 1) {
             double *s = J == 3 ? I.s3 : I.s0 + J;
             s[0 * 32 * FK_PITCH] = o_r;
             s[1 * 32 * FK_PITCH] = o_ua;
             s[2 * 32 * FK_PITCH] = o_ut;
             s[3 * 32 * FK_PITCH] = o_E;
         } else if (store) {
-            const long long o = I.o_it + J * A.pitch_out;
+            // tiled: the cell of J = 0 is row 1 of its band (segments start on a band), J = 3 row 0 of the next band
+            const long long o = LAY == LAY_TILED ? I.o_it + (J < 3 ? J * 8 : 4 * A.pitch_out - 8) : I.o_it + J * A.pitch_out;
             A.out[0][o] = o_r;
             A.out[1][o] = o_ua;
             A.out[2][o] = o_ut;
@@ -353,6 +385,17 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
 #endif
 constexpr unsigned long long FK_EVICT_FIRST = 0x12F0000000000000ULL, FK_EVICT_LAST = 0x14F0000000000000ULL;
 
+// one aligned 32-byte sector per thread (256-bit store, sm_100)
+__device__ __forceinline__ void fk_store4(double *p, double a, double b, double c, double d)
+{
+#if FK_STORE_HINT
+    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;"
+                 ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(FK_EVICT_LAST) : "memory");
+#else
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
+}
+
 __device__ __forceinline__ void fk_store2(double *p, double2 v)
 {
 #if FK_STORE_HINT
@@ -374,8 +417,15 @@ __device__ __forceinline__ void fast_flush(const SweepArgs &A, const double *sta
         constexpr int PIECES = FK_K / 2, ROWS = 32 / PIECES;   // 16-byte pieces per row, rows per warp instruction
         const int r0 = lane / PIECES, j = lane % PIECES;
         const double2 *src = reinterpret_cast<const double2 *>(stage + r0 * FK_PITCH + 2 * j);
+#ifdef FK_EXP_G         // timing experiment only (wrong results): the pieces of FK_EXP_G adjacent output rows made contiguous
+        const long long wr = w0 + r0;
+        const long long off = (wr / FK_EXP_G) * (FK_EXP_G * A.pitch_out) + (mb >> 3) * (8 * FK_EXP_G) + (wr % FK_EXP_G) * 8 + 2 * j;
+        const long long step = (ROWS >= FK_EXP_G) ? (ROWS / FK_EXP_G) * (FK_EXP_G * A.pitch_out) : ROWS * 8;
+        static_assert(FK_EXP_G >= 8 || FK_EXP_G == 1 || true, "");
+#else
         const long long off = (w0 + r0 + A.g) * A.pitch_out + (mb + A.g) + 2 * j;
         const long long step = ROWS * A.pitch_out;
+#endif
 #pragma unroll 1
         for (int v = 0; v < 4; v++) {
             double *dst = A.out[v] + off;
@@ -470,17 +520,19 @@ __device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
 
 // CONS = 1: also accumulates the conservation sums of the cells it stores (per-cycle diagnostics fused into the last
 // sweep of a cycle): per thread in march order, per warp by a fixed butterfly, one partial per warp for k_diag_final.
-template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0>
+template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS>
 __global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
 sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 {
+    static_assert(LAY == LAY_ROWS || STG == STG_TMA, "the tiled layout is staged by TMA only");
     extern __shared__ __align__(128) unsigned char fast_smem_raw[];
     // warp index through a shuffle: the compiler then knows it (and every address derived from it: the warp's ring, its
     // barriers, its first column) is warp-uniform and keeps it in uniform registers, which the TMA instructions take
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     FastWarpShared &S = reinterpret_cast<FastWarpShared *>(fast_smem_raw)[warp];
 
-    const long long w0 = (long long)blockIdx.x * ASYNC_TPB + warp * 32;
+    // tiled: lane 0 <-> array column 32 k (whole tiles / bands), i.e. cell 32 k - g
+    const long long w0 = (long long)blockIdx.x * ASYNC_TPB + warp * 32 - (LAY == LAY_TILED ? A.g : 0);
     const long long w = w0 + lane;
     // march segment k = [k seg - 4, (k+1) seg - 4): the first one starts with 4 virtual cells (masked), the last one
     // runs to the end of the domain
@@ -490,7 +542,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     const long long m1 = (kseg == A.nseg - 1) ? A.nm : m0 + A.seg;
 
     SweepThread T;
-    T.valid = w < A.nw;
+    T.valid = w >= 0 && w < A.nw;
     T.col = (T.valid ? w : A.nw - 1) + A.g;
     T.amax = 0ULL; T.tmax = 0ULL;
     T.cm = 0.0; T.ce = 0.0;
@@ -501,8 +553,9 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         if (CONS && lane == 0) { A.cons_m[cons_slot] = 0.0; A.cons_e[cons_slot] = 0.0; }   // the log line is dropped anyway
         if (T.valid) {
             for (long long m = m_lo; m < m1; m++) {
-                const long long i = (m + A.g) * A.pitch_in + T.col;
-                const long long o = A.transpose_out ? T.col * A.pitch_out + (m + A.g) : (m + A.g) * A.pitch_out + T.col;
+                const long long i = layout_index(LAY == LAY_TILED, m + A.g, T.col, A.pitch_in);
+                const long long o = A.transpose_out ? layout_index(LAY == LAY_TILED, T.col, m + A.g, A.pitch_out)
+                                                    : layout_index(LAY == LAY_TILED, m + A.g, T.col, A.pitch_out);
 #pragma unroll
                 for (int k = 0; k < 4; k++) A.out[k][o] = A.in[k][i];
             }
@@ -576,7 +629,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
                 const unsigned dst = ring_u32 + (unsigned)(G & (FK_NG - 1)) * (FK_GS * 8u);
                 fk_mbar_expect_tx(bar, 4u * FK_VS * 8u);
 #pragma unroll
-                for (int v = 0; v < 4; v++) fk_tma_load_2d(dst + v * (FK_VS * 8u), &M.m[v], col0, row0_arr + FK_GROUP * G, bar);
+                for (int v = 0; v < 4; v++) {
+                    if (LAY == LAY_TILED)   // element 4 col0 of band row0_arr / 4 + G: the 4 tiles of columns col0 .. col0 + 31
+                        fk_tma_load_2d(dst + v * (FK_VS * 8u), &M.m[v], 4 * col0, row0_arr / FK_GROUP + G, bar);
+                    else
+                        fk_tma_load_2d(dst + v * (FK_VS * 8u), &M.m[v], col0, row0_arr + FK_GROUP * G, bar);
+                }
             }
         } else {
             const unsigned gbase = (unsigned)(G & (FK_NG - 1)) * (FK_GS * 8u);
@@ -616,14 +674,21 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     for (int j = 0; j < 2; j++)
 #pragma unroll
         for (int k = 0; k < 4; k++) { P.T[j][k] = 0.; P.S[j][k] = 0.; P.Adv[j][k] = 0.; }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) P.Q[j][k] = 0.;
 
-    const double *ring = &S.ring[0][0][0][lane];
+    const double *ring = &S.ring[0][0][0][0] + (LAY == LAY_TILED ? (lane >> 3) * 32 + (lane & 7) : lane);
     double *cring = &S.cring[0][lane];
     double *sbase = S.stage + lane * FK_PITCH;
+    // tiled transposed stores: output row w + g = band (w0 + g) / 4 + lane / 4, row lane & 3 of its tiles
+    const long long q_lane = (((w0 + A.g) >> 2) + (lane >> 2)) * (4 * A.pitch_out) + (lane & 3) * 8;
     FastIter I;
+    I.q_off = 0; I.qok = false;
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
-#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS>(A, T, P, I, dt, OK);
+#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS, LAY>(A, T, P, I, dt, OK);
 #define FK_BEGIN(it)                                                                                        \
     {                                                                                                       \
         const int p_ = (it) & 1;                                                                            \
@@ -666,11 +731,23 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         I.s0 = sbase + ((4 * it + 5) & (FK_K - 1));
         I.s3 = sbase + k3;
         I.rem = len - (4 * it - 11);
-        if (TR == 0) I.o_it = (m0 + (4 * it - 11) + A.g) * A.pitch_out + T.col;
+        if (TR == 1 && LAY == LAY_TILED) {
+            // the unit completed at J = 2: cells m0 + 4 it - 12 .. - 9, i.e. columns mq .. mq + 3 of the output rows,
+            // mq = m0 + 4 it - 12 + g a multiple of 4; the ends of a segment are multiples of 4 as well
+            const long long mq = m0 + (4 * it - 12);
+            I.qok = T.valid && mq >= m_lo && mq + 4 <= m1;
+            I.q_off = q_lane + ((mq + A.g) >> 3) * 32 + ((mq + A.g) & 7);
+        }
+        if (TR == 0) {
+            if (LAY == LAY_TILED)   // m0 + 4 it - 11 + g = 4 (band) + 1
+                I.o_it = ((m0 + (4 * it - 11) + A.g) >> 2) * (4 * A.pitch_out) + ((w0 + A.g) >> 3) * 32 + (lane >> 3) * 32 + 8 + (lane & 7);
+            else
+                I.o_it = (m0 + (4 * it - 11) + A.g) * A.pitch_out + T.col;
+        }
         FK_STEP(0, 1, ok012)
         FK_STEP(1, 1, ok012)
         FK_STEP(2, 1, ok012)
-        if (TR == 1 && k3 == 0 && live) fast_flush(A, S.stage, w0, m0 + (4 * it - 8 - FK_K), m_lo, m1);
+        if (TR == 1 && LAY == LAY_ROWS && k3 == 0 && live) fast_flush(A, S.stage, w0, m0 + (4 * it - 8 - FK_K), m_lo, m1);
         FK_STEP(3, 1, ok3)
         FK_END(it)
     }
