@@ -1579,6 +1579,14 @@ int armon_solver_sweep_launches(armon_solver *s, uint64_t *count)
     return ARMON_OK;
 }
 
+int armon_solver_tiled(armon_solver *s, int32_t *tiled)
+{
+    if (int rc = solver_check(s, false, false)) return rc;
+    ARMON_CHECK_ARG(tiled != nullptr, "null result");
+    *tiled = s->group->tiled;
+    return ARMON_OK;
+}
+
 int armon_solver_diagnostics(armon_solver *s, int32_t capacity)
 {
     if (int rc = solver_check(s)) return rc;

@@ -296,6 +296,7 @@ class GpuJob:
                 "value": self.global_cells * steps / elapsed_s / 1e9}
 
     def roofline(self, run, clocks_mhz):
+        from armon_jl_b200.backend import check
         peak, peak_src = measured_peak()
         avg_s = run["sweep_ms"] / max(run["sweep_n"], 1) / 1e3
         achieved = BYTES_PER_CELL_SWEEP * self.local_cells / avg_s / 1e9
@@ -304,6 +305,11 @@ class GpuJob:
         kname = {"tma": "sweep_fast_kernel<STG_TMA", "async2": "sweep_fast_kernel<STG_CPA16",
                  "async": "sweep_async_kernel<sd, DIV_FLAGGED",
                  "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}[variant]
+        # which layout the fused path actually ran in (sweep_fast_kernel.cuh 5.): asked from the library, not assumed
+        tiled = C.c_int32(-1)
+        check(self.lib.armon_solver_tiled(self.grid.solver, C.byref(tiled)))
+        if tiled.value == 1:
+            variant, kname = "tiled", "sweep_fast_kernel<STG_TMA, LAY_TILED"
         key = f"{variant}_{self.math}_{'biz' if biz else 'pg'}"
         traffic = load_profile_json("sweep_traffic.json") or {}
         t = traffic.get(key)

@@ -269,6 +269,12 @@ int armon_solver_profile(armon_solver *solver, int enable);
 int armon_solver_sweep_time_ms(armon_solver *solver, double *total_ms, uint64_t *count);
 /* kernel + launch statistics of the fused path */
 int armon_solver_sweep_launches(armon_solver *solver, uint64_t *count);
+/* Layout the state is kept in between the sweeps of the fused path (no reference counterpart: the reference keeps one
+ * row-major layout and strides through it, src/blocking/blocking.jl:148-172): *tiled = 1 when the solver's group runs
+ * the band-tiled layout (fast mode, TMA staging, every block and every rank with extents that are multiples of 8;
+ * ARMON_B200_TILED=0 disables), 0 when it runs the row-major / transposed pair, -1 before the first cycle decided it.
+ * The arrays the caller sees (armon_solver_bind, after armon_solver_finalize) are always in the canonical layout. */
+int armon_solver_tiled(armon_solver *solver, int32_t *tiled);
 
 /* Per-cycle diagnostics without a host round trip: the reference's `silent <= 1` log line (src/solver.jl:359-371:
  * wait + conservation_vars + print after every cycle).  While enabled, every cycle enqueues a fixed-tree reduction of

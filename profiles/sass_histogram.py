@@ -53,6 +53,8 @@ def histogram(obj, pat):
 PRODUCT = {
     "tma_fast_pg": ("sweep_fast_inst_tma_pg.o", "sweep_fast_kernelILi0ELi2ELi1ELi0ELi1E"),
     "tma_fast_biz": ("sweep_fast_inst_tma_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1E"),
+    "tiled_fast_pg": ("sweep_fast_inst_tiled_pg.o", "sweep_fast_kernelILi0ELi2ELi1ELi0ELi1ELi0ELi1E"),
+    "tiled_fast_biz": ("sweep_fast_inst_tiled_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1ELi0ELi1E"),
     "async2_fast_pg": ("sweep_fast_inst_cpa16_pg.o", "sweep_fast_kernelILi1ELi2ELi1ELi0ELi1E"),
     "async2_fast_biz": ("sweep_fast_inst_cpa16_biz.o", "sweep_fast_kernelILi1ELi2ELi1ELi1ELi1E"),
     "async_strict_pg": ("sweep_async_inst_strict_pg.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi0ELi1E"),

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Reduce an ncu report (.ncu-rep, `--set full`) to the metrics quoted in DESIGN.md / profiles/README.md.
 
-  python profiles/summarize.py gpurun_out/prof.ncu-rep profiles/out_summary.csv [--traffic profiles/sweep_traffic.json]
+  python profiles/summarize.py gpurun_out/prof.ncu-rep profiles/out_summary.csv \
+         [--traffic profiles/sweep_traffic.json --key tiled_fast_pg --cells 268435456]
 """
 import csv
 import json
@@ -39,13 +40,21 @@ def main():
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd = float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]]
         wr = float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]]
-        with open(sys.argv[sys.argv.index("--traffic") + 1], "w") as f:
-            cells = int(sys.argv[sys.argv.index("--cells") + 1]) if "--cells" in sys.argv else 8192 * 8192
-            json.dump({"kernel": d["Kernel Name"], "grid": d["Grid Size"], "dram_bytes_read": rd, "dram_bytes_write": wr,
-                       "bytes_per_launch": rd + wr, "cells_per_launch": cells, "algorithmic_bytes_per_launch": 64 * cells,
-                       "source": rep.split("/")[-1],
-                       "note": "ncu --set full --clock-control none, one launch of the sweep kernel at 8192x8192"}, f, indent=1)
-
+        path = sys.argv[sys.argv.index("--traffic") + 1]
+        key = sys.argv[sys.argv.index("--key") + 1]        # <kernel>_<math>_<eos>, as bench.py looks it up
+        cells = int(sys.argv[sys.argv.index("--cells") + 1])
+        try:
+            with open(path) as f:
+                allk = json.load(f)
+        except FileNotFoundError:
+            allk = {}
+        allk[key] = {"kernel": d["Kernel Name"], "grid": d["Grid Size"],
+                     "duration_ms_under_ncu": float(d["gpu__time_duration.sum"]),
+                     "dram_bytes_read": rd, "dram_bytes_write": wr, "bytes_per_launch": rd + wr, "cells_per_launch": cells,
+                     "algorithmic_bytes_per_launch": 64 * cells, "traffic_over_algorithmic": (rd + wr) / (64 * cells),
+                     "source": rep.split("/")[-1]}
+        with open(path, "w") as f:
+            json.dump(allk, f, indent=1)
 
 if __name__ == "__main__":
     main()

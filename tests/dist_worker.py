@@ -194,9 +194,14 @@ def run_gpu(args):
              # and must run with the edge launches of the overlapped sweep
              ("Sod_circ", (107, 113), 12, "strict", "Sequential", 16),
              ("Sod_circ", (50 * world, 50 * world), 10, "strict", "Sequential", 16),
-             ("Sod_circ", (50 * world, 50 * world), 10, "fast", "Godunov", 16)]
+             ("Sod_circ", (50 * world, 50 * world), 10, "fast", "Godunov", 16),
+             # band-tiled layout of the fast mode (local extents multiples of 8): ghost bands through NCCL, sweeps that
+             # keep their axis (Godunov splitting); and a decomposition where only SOME ranks could tile (64 + 65 columns
+             # on 2 ranks): the ranks must agree not to, the ghost bands travel as raw memory
+             ("Sod_circ", (64 * world, 128), 11, "fast", "Godunov", 0),
+             ("Sod_circ", (64 * world + 1, 64), 10, "fast", "Sequential", 0)]
     if args.quick:
-        cases = [cases[0], cases[5]]
+        cases = [cases[0], cases[5], cases[7]]
     for test, global_n, cycles, math, splitting, segment in cases:
         kw = dict(test=test, N=global_n, maxcycle=cycles, math_mode=math, axis_splitting=splitting,
                   march_segment=segment, return_data=True, **SCHEME)

@@ -130,3 +130,27 @@ def test_tiled_layout_diagnostics_and_restart():
     for (c1, m1, e1), (c0, m0, e0) in zip(lines[True][0], lines[False][0]):
         assert c1 == c0 and abs(m1 - m0) <= 1e-14 * abs(m0) and abs(e1 - e0) <= 1e-14 * abs(e0)
     assert_same(lines[True][1], lines[False][1], "rho")
+
+
+def test_tiled_layout_cycles_past_the_end_and_graph_replay():
+    """The copy-through of a finished run (cycles enqueued past maxcycle) and the CUDA-graph replay of cycle pairs in the
+    tiled layout: same bits as the plain run, stale p and c included."""
+    kw = dict(N=(128, 64), maxcycle=9, math_mode="fast")
+    os.environ["ARMON_B200_TILED"] = "1"
+    try:
+        s0 = armon.armon(reference_params("Sod_circ", cuda_graph="off", return_data=True, **kw))
+        s1 = armon.armon(reference_params("Sod_circ", cuda_graph="on", return_data=True, **kw))
+        p2 = reference_params("Sod_circ", cuda_graph="off", **kw)
+        g2 = armon.BlockGrid(p2)
+        armon.init_test(p2, g2)
+        g2.run(14)                                  # 5 cycles past the end
+        st = g2.time_state()
+        assert st.done and st.cycle == 9 and st.time == s0.final_time
+        assert s1.cycles == s0.cycles == 9 and s1.last_dt == s0.last_dt
+        for v in VARS:
+            assert_same(s1.data.real(v), s0.data.real(v), f"{v}: graph replay")
+            if v != "g":
+                assert_same(g2.real(v), s0.data.real(v), f"{v}: past the end")
+        s0.data.close(); s1.data.close(); g2.close()
+    finally:
+        del os.environ["ARMON_B200_TILED"]
