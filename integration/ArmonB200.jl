@@ -279,6 +279,15 @@ function device_time_loop(params::ArmonParameters{<:Any, <:B200Device}, grid::Bl
     end
 end
 
+# Layout of the state between the sweeps of the fused loop (include/armon_b200.h: armon_solver_tiled): 1 band-tiled,
+# 0 row-major / transposed pair, -1 not decided yet (before the first cycle).  Informational: the arrays Julia sees are
+# canonical whenever `ensure_canonical` has run; ENV["ARMON_B200_TILED"] = "0" keeps the row-major layouts.
+function fused_layout_is_tiled(params::ArmonParameters{<:Any, <:B200Device}, grid::BlockGrid)
+    tiled = Ref{Int32}(-1)
+    @b200call(:armon_solver_tiled, (Ptr{Cvoid}, Ptr{Int32}), fused_solver(params, grid), tiled)
+    tiled[]
+end
+
 # ------------------------------------------------------------------------------------------------------------
 # Seam 2b: per-step overloads (debug / `compare=true` checkpoints, src/io.jl:185-227): one ccall per
 # `@generic_kernel`, same per-block wrapper signatures as the reference (src/kernels.jl:151-230,
