@@ -210,7 +210,7 @@ struct FastIter {
     bool qok;                    // ... and whether it is stored (real column, unit inside the segment)
 };
 
-__device__ __forceinline__ void fk_store4(double *p, double a, double b, double c, double d);
+__device__ __forceinline__ void fk_store4_if(bool ok, double *p, double a, double b, double c, double d);
 
 // One march step at cell a; J = (a - a_begin) & 3 static.  EMIT / TR compile-time as in march_compute2; `ok`: the
 // thread's column holds a real cell (false also for the steps that run the emitting code on cells before the segment,
@@ -344,9 +344,9 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
             // store per variable: no shared-memory staging, no flush phase that stalls the warp every 8 steps.
             constexpr int SL = (J + 1) & 3;
             P.Q[0][SL] = o_r; P.Q[1][SL] = o_ua; P.Q[2][SL] = o_ut; P.Q[3][SL] = o_E;
-            if (J == 2 && I.qok) {
+            if (J == 2) {   // predicated stores, not a branch around them: the step stays one basic block
 #pragma unroll
-                for (int v = 0; v < 4; v++) fk_store4(A.out[v] + I.q_off, P.Q[v][0], P.Q[v][1], P.Q[v][2], P.Q[v][3]);
+                for (int v = 0; v < 4; v++) fk_store4_if(I.qok, A.out[v] + I.q_off, P.Q[v][0], P.Q[v][1], P.Q[v][2], P.Q[v][3]);
             }
         } else if (TR == 1) {
             double *s = J == 3 ? I.s3 : I.s0 + J;
@@ -386,14 +386,16 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
 #endif
 constexpr unsigned long long FK_EVICT_FIRST = 0x12F0000000000000ULL, FK_EVICT_LAST = 0x14F0000000000000ULL;
 
-// one aligned 32-byte sector per thread (256-bit store, sm_100)
-__device__ __forceinline__ void fk_store4(double *p, double a, double b, double c, double d)
+// one aligned 32-byte sector per thread (256-bit store, sm_100), predicated on `ok`
+__device__ __forceinline__ void fk_store4_if(bool ok, double *p, double a, double b, double c, double d)
 {
 #if FK_STORE_HINT
-    asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;"
-                 ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(FK_EVICT_LAST) : "memory");
+    asm volatile("{\n.reg .pred pq;\nsetp.ne.s32 pq, %6, 0;\n"
+                 "@pq st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;\n}"
+                 ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "l"(FK_EVICT_LAST), "r"((int)ok) : "memory");
 #else
-    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    asm volatile("{\n.reg .pred pq;\nsetp.ne.s32 pq, %5, 0;\n@pq st.global.v4.f64 [%0], {%1, %2, %3, %4};\n}"
+                 ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d), "r"((int)ok) : "memory");
 #endif
 }
 
