@@ -480,6 +480,20 @@ __device__ __forceinline__ void fk_mbar_wait(unsigned bar, unsigned parity)
         if (!done && ++spins > (1u << 24)) __trap();
     } while (!done);
 }
+// Non-blocking test of the same phase.  The phase check is a long-latency instruction even when the copies landed long
+// ago; issued two steps before the group is needed, its result is there when the next iteration starts and the blocking
+// wait is skipped (the profile showed 2.7 % of the warp samples sitting on the check at the top of the iteration).
+__device__ __forceinline__ bool fk_mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
+}
 // One lane of the (converged) warp: elect.sync tells the compiler that exactly one thread runs the guarded code, so the
 // TMA instructions inside are issued straight from uniform registers (a `lane == 0` test makes it wrap each of them in
 // a loop over the active lanes).
@@ -698,9 +712,13 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         I.gb0 = ring + ((it) & (FK_NG - 1)) * FK_GS;                                                        \
         I.cw = cring + p_ * 4 * 32;                                                                         \
         I.cr = cring + (p_ ^ 1) * 4 * 32;                                                                   \
-        if (STG == STG_TMA) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
-        else { async_wait<3>(); __syncwarp(); }                                                             \
+        if (STG == STG_TMA) {                                                                               \
+            if (!landed) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
+        } else { async_wait<3>(); __syncwarp(); }                                                           \
     }
+    /* early look at the barrier of the next iteration's group */
+#define FK_PEEK(it)                                                                                         \
+    if (STG == STG_TMA) landed = fk_mbar_test(bar_u32 + 8u * (unsigned)(((it) + 1) & (FK_NG - 1)), (unsigned)((((it) + 1) >> 2) & 1));
 #define FK_END(it)                                                                                          \
     {                                                                                                       \
         __syncwarp();   /* every lane has read the last row of group it: refill its slot */                 \
@@ -709,11 +727,13 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 
     // warm-up: steps 0 .. 7 fill the head of the dependency cone of the first output, nothing is emitted
     int it = 0;
+    bool landed = false;
 #pragma unroll 1
     for (; it < 2; it++) {
         FK_BEGIN(it)
         FK_STEP(0, 0, false)
         FK_STEP(1, 0, false)
+        FK_PEEK(it)
         FK_STEP(2, 0, false)
         FK_STEP(3, 0, false)
         FK_END(it)
@@ -749,12 +769,14 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         }
         FK_STEP(0, 1, ok012)
         FK_STEP(1, 1, ok012)
+        FK_PEEK(it)
         FK_STEP(2, 1, ok012)
         if (TR == 1 && LAY == LAY_ROWS && k3 == 0 && live) fast_flush(A, S.stage, w0, m0 + (4 * it - 8 - FK_K), m_lo, m1);
         FK_STEP(3, 1, ok3)
         FK_END(it)
     }
 #undef FK_STEP
+#undef FK_PEEK
 #undef FK_BEGIN
 #undef FK_END
     if (STG != STG_TMA) async_wait<0>();
