@@ -123,11 +123,19 @@ __device__ __forceinline__ double xclamp01(double r)
 template <int LIMITER> __device__ __forceinline__ double xlimiter(double r)
 {
     if (LIMITER == ARMON_LIMITER_MINMOD) return xclamp01(r);
-    if (LIMITER == ARMON_LIMITER_SUPERBEE) {   // max(0, min(2r, 1), min(r, 2)), src/limiters.jl:8
+    if (LIMITER == ARMON_LIMITER_SUPERBEE) {
+        // max(0, min(2r, 1), min(r, 2)) (src/limiters.jl:8) selected by the bit pattern like the minmod clamp, off the
+        // FP64 pipe:  r < 0, -0 -> +0 | r < 1/2 -> 2r | r < 1 -> 1 | r < 2 -> r | r >= 2, NaN -> 2
+        const int hi = __double2hiint(r), lo = __double2loint(r);
         const double r2 = xadd(r, r);
-        const double a = r2 < 1.0 ? r2 : 1.0, b = r < 2.0 ? r : 2.0;
-        const double m = a < b ? b : a;
-        return 0.0 < m ? m : 0.0;
+        const bool small = hi < 0x3fe00000;                            // signed: r < 1/2, negative r included
+        const bool mid = (unsigned)(hi - 0x3ff00000) < 0x00100000u;    // 1 <= r < 2
+        const bool neg = hi < 0;
+        int oh = min(max(hi, 0x3ff00000), 0x40000000);                 // r >= 1/2: clamped to [1, 2]
+        int ol = mid ? lo : 0;
+        oh = small ? __double2hiint(r2) : oh;
+        ol = small ? __double2loint(r2) : ol;
+        return __hiloint2double(neg ? 0 : oh, neg ? 0 : ol);
     }
     return 1.0;
 }
