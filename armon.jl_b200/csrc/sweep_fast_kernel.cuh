@@ -428,11 +428,14 @@ __device__ __forceinline__ void fast_flush(const SweepArgs &A, const double *sta
         constexpr int PIECES = FK_K / 2, ROWS = 32 / PIECES;   // 16-byte pieces per row, rows per warp instruction
         const int r0 = lane / PIECES, j = lane % PIECES;
         const double2 *src = reinterpret_cast<const double2 *>(stage + r0 * FK_PITCH + 2 * j);
-#ifdef FK_EXP_G         // timing experiment only (wrong results): the pieces of FK_EXP_G adjacent output rows made contiguous
+#ifdef FK_EXP_G
+        // TIMING EXPERIMENT ONLY, never defined in the product build (the results are wrong): the same flush, but the
+        // 64-byte pieces of FK_EXP_G (2, 4, 8 or 32) adjacent output rows are written next to each other.  It measured
+        // what the piece length of the transposed stores costs (profiles/README.md) and led to the tiled layout.
+        static_assert(FK_EXP_G == 2 || FK_EXP_G == 4 || FK_EXP_G == 8 || FK_EXP_G == 32, "experiment sizes");
         const long long wr = w0 + r0;
         const long long off = (wr / FK_EXP_G) * (FK_EXP_G * A.pitch_out) + (mb >> 3) * (8 * FK_EXP_G) + (wr % FK_EXP_G) * 8 + 2 * j;
         const long long step = (ROWS >= FK_EXP_G) ? (ROWS / FK_EXP_G) * (FK_EXP_G * A.pitch_out) : ROWS * 8;
-        static_assert(FK_EXP_G >= 8 || FK_EXP_G == 1 || true, "");
 #else
         const long long off = (w0 + r0 + A.g) * A.pitch_out + (mb + A.g) + 2 * j;
         const long long step = ROWS * A.pitch_out;
