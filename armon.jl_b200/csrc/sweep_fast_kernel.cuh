@@ -43,9 +43,12 @@
 //    transposed output of 4. leaves a warp as isolated 64-byte pieces 128 KB apart; measured on the Godunov sweep
 //    (memory-bound), that store pattern caps a transposing sweep at 0.77 of the copy bandwidth whatever the arithmetic
 //    (pieces of 128 B: 0.79, 256 B: 0.865, 512 B: 0.87, 2 KB: 0.89 -- profiles/README.md).  In the tiled layout
-//    (common.cuh, tiled_index: bands of 4 rows, tiles of [4 rows][8 columns]) the same flush writes the 4 rows of a band
-//    as one contiguous 256-byte tile, and the next sweep fetches a [4 rows x 32 columns] staging group as one contiguous
-//    1 KB run (4 adjacent tiles) instead of 4 row pieces.  Threads are shifted by 4 columns (lane 0 of a warp <-> array
+//    (common.cuh, tiled_index: bands of 4 rows, tiles of [4 rows][8 columns]) 4 consecutive march cells of a thread are
+//    one aligned 32-byte unit of its output row and the 4 rows of a band x 8 cells one contiguous 256-byte tile: the
+//    transposed output leaves the REGISTERS as one predicated 256-bit store per variable every 4 steps (no staging tile,
+//    no flush phase -- a staged flush of the same tiles stalled the in-order warp ~280 clocks every 8 steps and was no
+//    faster than row-major on the FP64-heavy sweeps), and the next sweep fetches a [4 rows x 32 columns] staging group as
+//    one contiguous 1 KB run (4 adjacent tiles) instead of 4 row pieces.  0.77 -> 0.92 of the copy bandwidth.  Threads are shifted by 4 columns (lane 0 of a warp <-> array
 //    column 32 k, i.e. cell 32 k - 4) so that a warp's columns are whole tiles on the input side and whole bands on the
 //    output side; the 4 ghost columns this brings into the first warp are masked like the ragged tail.  The arithmetic
 //    is untouched: results are bit-identical to the row-major path.  The ghost rows of a side are exactly one band, so

@@ -294,7 +294,8 @@ def test_conservation_vars_match_oracle(test, N):
 
 @pytest.mark.parametrize("N,blocks,mode", [((96, 80), (1, 1), "strict"), ((96, 80), (2, 3), "strict"),
                                            ((96, 80), (1, 1), "fast"), ((96, 80), (2, 3), "fast"),
-                                           ((97, 81), (1, 1), "fast"), ((130, 75), (3, 1), "fast")])
+                                           ((97, 81), (1, 1), "fast"), ((130, 75), (3, 1), "fast"),
+                                           ((128, 96), (2, 2), "fast")])   # 64x48 blocks: tiled layout + fused sums
 def test_per_cycle_diagnostics_ring(N, blocks, mode, capsys):
     """The `silent <= 1` log (src/solver.jl:359-371) produced on the device: one line per cycle, same cycle / time / dt
     as the time-step state, mass and energy equal to conservation_vars of that cycle's state.  In fast mode with even
