@@ -232,6 +232,14 @@ class BlockGrid:
         self._call("read_diagnostics", lines, max_lines, C.byref(n))
         return [(ln.cycle, ln.time, ln.dt, ln.mass, ln.energy) for ln in lines[:n.value]]
 
+    def fused_layout_is_tiled(self):
+        """Layout of the state between the sweeps of the fused loop (armon_solver_tiled): 1 band-tiled, 0 row-major /
+        transposed pair, -1 not decided yet (before the first cycle).  The arrays this object hands out are canonical
+        either way."""
+        tiled = C.c_int32(-1)
+        check(self.lib.armon_solver_tiled(self.blocks[0].solver, C.byref(tiled)), "armon_solver_tiled")
+        return tiled.value
+
     def reset(self):                                # reset!(grid, params), src/blocking/block_grid.jl:555-561
         self.global_dt.reset(self.params)
         self.state.reset()

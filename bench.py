@@ -306,9 +306,7 @@ class GpuJob:
                  "async": "sweep_async_kernel<sd, DIV_FLAGGED",
                  "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}[variant]
         # which layout the fused path actually ran in (sweep_fast_kernel.cuh 5.): asked from the library, not assumed
-        tiled = C.c_int32(-1)
-        check(self.lib.armon_solver_tiled(self.grid.solver, C.byref(tiled)))
-        if tiled.value == 1:
+        if self.grid.fused_layout_is_tiled() == 1:
             variant, kname = "tiled", "sweep_fast_kernel<STG_TMA, LAY_TILED"
         key = f"{variant}_{self.math}_{'biz' if biz else 'pg'}"
         traffic = load_profile_json("sweep_traffic.json") or {}

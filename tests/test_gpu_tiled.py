@@ -31,6 +31,7 @@ def run(params, tiled):
         params.return_data = True
         stats = armon.armon(params)
         grid = stats.data
+        assert grid.fused_layout_is_tiled() == (1 if tiled else 0)      # the layout asked for is the layout that ran
         out = {v: grid.real(v).copy() for v in VARS}
         grid.close()
     finally:
