@@ -371,6 +371,9 @@ struct armon_solver {
     bool              use_fast = false;
     int               fast_stg = STG_TMA;
     sweep_fast_fn_t   fast_cons_kernel[2] = {nullptr, nullptr};   // TMA staging + conservation sums, [transposed output]
+    // strict arithmetic on the fast kernel's schedule (sweep_fast_kernel.cuh 6.), [transposed output]; even pitches
+    sweep_fast_fn_t   strict4_kernel[2] = {nullptr, nullptr};
+    bool              use_strict4 = false;
     // per-cycle diagnostics: this block's region of the group's partial-sum scratch, and whether the last sweep of the
     // cycle being enqueued filled it itself (fused) or k_diag_rows has to
     long long         diag_base = 0, diag_cap = 0;
@@ -557,7 +560,7 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         int seg = (s->d.march_segment + 15) / 16 * 16;
         return seg;
     }
-    if (s->use_fast) {
+    if (s->use_fast || (s->use_strict4 && ((nw + 2 * s->d.dims.g) % 2) == 0)) {
         // Fast kernels (8 warps = 2 CTAs per SM): every CTA marches seg + 12 rows (the warm-up rows of a segment are
         // redundant work) and the CTAs run in waves of 2 x SMs, so the sweep costs about waves x (seg + 12) row times.
         // Take the multiple of 16 that minimises it -- a power of two can sit just above a whole number of waves (the
@@ -682,7 +685,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     const bool has_nb = s->d.neighbours[lo_side] >= 0 || s->d.neighbours[hi_side] >= 0;
     // (the fast kernels cut their segments 4 cells earlier -- 64-byte aligned transposed stores -- so their last
     // segment is never shorter than 5 cells)
-    const bool short_tail = !s->use_fast && A.nm - (nseg - 1) * A.seg < A.g;
+    // strict arithmetic on the fast kernel's schedule: TMA staging needs 16-byte aligned rows (even pitch)
+    const bool strict4_launch = s->use_strict4 && (A.pitch_in % 2) == 0 && s->strict4_kernel[A.transpose_out ? 1 : 0] != nullptr;
+    const bool short_tail = !(s->use_fast || strict4_launch) && A.nm - (nseg - 1) * A.seg < A.g;
     const long long n_interior = nseg - 2 - (short_tail ? 1 : 0);
     const bool overlap = has_nb && n_interior >= 1 && s->overlap;
     if (has_nb) {
@@ -692,13 +697,13 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         if (int rc = comm_end(s, !overlap)) return rc;
     }
 
-    const bool fast_launch = s->use_fast;
+    const bool fast_launch = s->use_fast || strict4_launch;
     const bool tiled = s->cur_tiled;   // layout of the input and of the output (ensure_layout ran before)
     if (tiled && !(fast_launch && s->tiled_ok)) {
         armon_set_error("internal: band-tiled state without the tiled kernels");
         return ARMON_ERR_INVALID;
     }
-    const int stg = tiled ? STG_TMA : (A.pitch_in % 2) == 0 ? s->fast_stg : STG_CPA8;
+    const int stg = (tiled || strict4_launch) ? STG_TMA : (A.pitch_in % 2) == 0 ? s->fast_stg : STG_CPA8;
     SweepTmaMaps maps;
     if (fast_launch && stg == STG_TMA) {
         for (int k = 0; k < 4; k++) {
@@ -711,7 +716,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     }
     const int tr = A.transpose_out ? 1 : 0;
     // per-cycle diagnostics: the last sweep of the cycle accumulates the conservation sums itself when it can
-    const bool cons = fast_launch && stg == STG_TMA && s->cons_m != nullptr &&
+    const bool cons = fast_launch && !strict4_launch && stg == STG_TMA && s->cons_m != nullptr &&
                       (tiled ? s->fast_tiled_cons_kernel[tr] : s->fast_cons_kernel[tr]) != nullptr;
     A.cons_m = cons ? s->cons_m : nullptr;
     A.cons_e = cons ? s->cons_e : nullptr;
@@ -732,7 +737,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         s->prof_used += 2;
         ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
     }
-    const bool with_fixup = staged_launch && s->fixup_kernel;
+    const bool with_fixup = (staged_launch || strict4_launch) && s->fixup_kernel;
     FixupArgs F;
     F.count = s->fix_count ? s->fix_count + (s->sweep_index & 1) : nullptr;
     F.count_next = s->fix_count ? s->fix_count + ((s->sweep_index + 1) & 1) : nullptr;
@@ -748,8 +753,9 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         // (tiled: the threads are shifted by the g ghost columns, sweep_fast_kernel.cuh 5.)
         const dim3 grid((unsigned)((A.nw + (tiled ? D.g : 0) + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
         if (fast_launch)
-            (tiled ? (cons ? s->fast_tiled_cons_kernel[tr] : s->fast_tiled_kernel[tr])
-                   : (cons ? s->fast_cons_kernel[tr] : s->fast_kernel[stg][tr]))
+            (strict4_launch ? s->strict4_kernel[tr]
+             : tiled ? (cons ? s->fast_tiled_cons_kernel[tr] : s->fast_tiled_kernel[tr])
+                     : (cons ? s->fast_cons_kernel[tr] : s->fast_kernel[stg][tr]))
                 <<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
         else if (staged_launch)
             s->staged_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->staged_smem, st>>>(A);
@@ -1066,6 +1072,8 @@ int read_state(armon_group *G, armon_time_state *out)
     out->error = h->error;
     out->done = h->done;
     out->error_cycle = h->error_cycle;
+    if (getenv("ARMON_B200_VERBOSE"))   // strict mode: column chunks handed to the IEEE fix-up so far
+        fprintf(stderr, "[armon_b200] cycle %lld: %u column chunks recomputed by the IEEE fix-up\n", h->cycle, h->redo_count);
     return ARMON_OK;
 }
 
@@ -1257,6 +1265,10 @@ void group_free_common(armon_group *G)
     if (G->agree) cudaFree(G->agree);
 }
 
+#ifndef ARMON_STRICT_CHAINS_DEFAULT
+#define ARMON_STRICT_CHAINS_DEFAULT false
+#endif
+
 // Select the marching kernels of a solver from its descriptor.
 int select_kernels(armon_solver *s)
 {
@@ -1353,6 +1365,24 @@ int select_kernels(armon_solver *s)
             }
         }
         s->use_staged = ok;
+    }
+    // ARMON_B200_STRICT=chains: the strict arithmetic on the four-chain schedule of the fast kernel (TMA staging);
+    // =async: the unskewed cp.async kernel
+    if (s->use_staged && desc->math_mode == ARMON_MATH_STRICT) {
+        const char *sk = getenv("ARMON_B200_STRICT");
+        const bool want = sk ? std::string(sk) == "chains" : ARMON_STRICT_CHAINS_DEFAULT;
+        bool ok = want;
+        for (int tr = 0; tr < 2 && want; tr++) {
+            sweep_fast_fn_t fn = biz ? sweep_fast_table_strict_biz(rl, desc->projection, tr) : sweep_fast_table_strict_pg(rl, desc->projection, tr);
+            s->strict4_kernel[tr] = fn;
+            ok = ok && fn != nullptr;
+            if (!fn) continue;
+            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(ASYNC_TPB / 32 * sizeof(FastWarpShared))));
+            ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+        }
+        s->use_strict4 = ok;
     }
     if (s->use_staged && desc->math_mode == ARMON_MATH_STRICT) {
         s->fixup_kernel = biz ? sweep_fixup_table_biz(rl, desc->projection) : sweep_fixup_table_pg(rl, desc->projection);

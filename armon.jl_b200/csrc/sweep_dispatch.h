@@ -89,17 +89,22 @@ sweep_fast_fn_t sweep_fast_table_tiled_biz(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_tiled_cons_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_tiled_cons_biz(int rl, int proj, int tr);
 
-#define ARMON_FAST_ROW(STG, RLV, EOS, CONS, LAY)                                             \
-    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS, LAY>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS, LAY>}, \
-     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS, LAY>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS, LAY>}}
+// strict arithmetic on the schedule of the fast kernel (MATH_STRICT: TMA staging, row-major layouts, four chains per step)
+sweep_fast_fn_t sweep_fast_table_strict_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_strict_biz(int rl, int proj, int tr);
 
-#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS, LAY)                                   \
+#define ARMON_FAST_ROW_M(STG, RLV, EOS, CONS, LAY, MATH)                                     \
+    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS, LAY, MATH>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS, LAY, MATH>}, \
+     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS, LAY, MATH>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS, LAY, MATH>}}
+
+#define ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH)                           \
     sweep_fast_fn_t NAME(int rl, int proj, int tr)                                          \
     {                                                                                       \
         static const sweep_fast_fn_t table[4][2][2] = {                                     \
-            ARMON_FAST_ROW(STG, 0, EOS, CONS, LAY), ARMON_FAST_ROW(STG, 1, EOS, CONS, LAY), \
-            ARMON_FAST_ROW(STG, 2, EOS, CONS, LAY), ARMON_FAST_ROW(STG, 3, EOS, CONS, LAY), \
+            ARMON_FAST_ROW_M(STG, 0, EOS, CONS, LAY, MATH), ARMON_FAST_ROW_M(STG, 1, EOS, CONS, LAY, MATH), \
+            ARMON_FAST_ROW_M(STG, 2, EOS, CONS, LAY, MATH), ARMON_FAST_ROW_M(STG, 3, EOS, CONS, LAY, MATH), \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \
     }
+#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS, LAY) ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH_FAST)

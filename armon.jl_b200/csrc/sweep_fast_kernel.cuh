@@ -57,10 +57,13 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "sweep_async_kernel.cuh"
 
 enum { STG_TMA = 0, STG_CPA16 = 1, STG_CPA8 = 2 };
 enum { LAY_ROWS = 0, LAY_TILED = 1 };          // layout of the input AND of the output of a sweep
+enum { MATH_FAST = 0, MATH_STRICT = 1 };       // arithmetic of the step: fast_step (section 2.) or strict_step (section 6.)
 
 // the four input arrays of a sweep (rho, ua, ut, E) as 2-D tensors: LAY_ROWS [array rows][pitch], box = 4 rows x 32
 // columns; LAY_TILED [bands][4 pitch], box = 1 band x 128 elements (4 adjacent tiles = the same 4 rows x 32 columns)
@@ -219,6 +222,9 @@ struct FastIter {
     int rem;                     // cells of the segment still to emit, counting the one of J = 0 (<= 0: none)
     long long q_off;             // tiled transposed stores: element offset of the 4-cell unit completed at J = 2
     bool qok;                    // ... and whether it is stored (real column, unit inside the segment)
+    unsigned row_mask;           // strict arithmetic: bit J set <=> row J of the current group exists in the array (the others
+                                 // were zero-filled by the copy engine and are given a benign state before use)
+    const double *gbm;           // strict_step: this lane's column of the ring group holding rows a-4-J .. (the previous group)
 };
 
 __device__ __forceinline__ void fk_store4_if(bool ok, double *p, double a, double b, double c, double d);
@@ -381,6 +387,225 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
     P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
     P.dl[Z0] = C_dl; P.dxl[Z0] = C_dxl; P.Lr[Z0] = C_Lr; P.Lru[Z0] = C_Lru; P.Lrt[Z0] = C_Lrt; P.LrE[Z0] = C_LrE;
 #undef ZS
+}
+
+// ---- 6. STRICT ARITHMETIC ON THE SAME SCHEDULE (MATH_STRICT) ---------------------------------------------------------
+// The bit-exact mode (math_mode strict) on the skeleton of this file: TMA staging, four independent chains per step.
+// The arithmetic is the reference's, operation for operation -- the expressions of march_compute<sd, DIV_FLAGGED>
+// (sweep_kernel.cuh), only evaluated at other steps: a chain reads what EARLIER steps committed, never a result of its
+// own step, so the in-order warp always has four dependency chains to interleave (the unskewed strict kernel runs EOS ->
+// Godunov -> GAD -> cell update -> advection -> projection as ONE chain of ~250 dependent FP64 operations per step and
+// spends two thirds of its issue slots waiting).  A cell's result is a function of its dependency cone only, so the
+// bits are those of the unskewed kernel and of the CPU oracle.  Row-major layouts (LAY_ROWS) only: the IEEE fix-up of
+// the out-of-range division operands (sweep_fixup_kernel.cuh) works on them.
+//
+// Rows outside the array (the 4 virtual cells before the first segment, the rows the last segment consumes past the
+// last ghost row) are zero-filled by the copy engine; they only feed cells that are never stored, but a zero density
+// would raise the thread's range flag and send real chunks to the fix-up: chain A replaces them by a benign state.
+struct PipeS {
+    sd cp[4], crc[4];                                       // cells a-1 .. a-3: p, rho c (what the EOS computed; rho, ua, ut
+                                                            // and E of the cells a-1 .. a-4 are re-read from the staging
+                                                            // ring, which keeps the previous group for that)
+    sd Gu[4], Gp[4];                                        // Godunov states of interfaces a-1 .. a-3
+    sd Fu[4], Fp[4], FpFu[4];                               // flux used (GAD or Godunov) of interfaces a-3, a-4, and p u
+    sd disp[4], dxl[4];                                     // interfaces / cells a-5 .. a-7: dt Fu, Lagrangian width
+    sd Lr[4], Lu[4], Lt[4], LE[4];                          // Lagrangian cells a-5 .. a-7: rho, ua, ut, E (the products
+                                                            // rho {ua, ut, E} are formed where they are used: same bits)
+    sd Ar, Aru, Art, ArE;                                   // advection flux of interface a-7
+    sd Sr, Sru, Srt, SrE;                                   // limited slopes of cell a-7
+    sd S2b, S2r;                                            // 2 dxl of cell a-7 and its refined reciprocal
+};
+
+template <int RL, int PROJ, int EOS, int J, int TR, int EMIT>
+__device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, PipeS &P, const FastIter &I, const sd dt,
+                                            const typename Div<sd, DIV_FLAGGED>::Rcp &inv_dx, const bool ok)
+{
+    typedef sd R;
+    typedef Div<sd, DIV_FLAGGED> D;
+#define ZS(k) ((J + 8 - (k)) & 3)
+    constexpr int Z0 = ZS(0), Z1 = ZS(1), Z2 = ZS(2), Z3 = ZS(3);   // also the slots of a-4, a-5, a-6, a-7
+    const R dx(A.dx);
+    RangeFlag &f = T.flag;
+    // rows a, a-1 .. a-4 of this lane's column: row J of the current group, or of the previous one (compile-time choice)
+    const double *row0 = I.gb0 + J * 32;
+    const double *row1 = J >= 1 ? I.gb0 + (J - 1) * 32 : I.gbm + (J + 3) * 32;
+    const double *row2 = J >= 2 ? I.gb0 + (J - 2) * 32 : I.gbm + (J + 2) * 32;
+    const double *row3 = J >= 3 ? I.gb0 + (J - 3) * 32 : I.gbm + (J + 1) * 32;
+    const double *row4 = I.gbm + J * 32;
+
+    // ---- chain A, cell a: EOS (src/kernels.jl:4-55), Godunov state of interface a (src/riemann_schemes.jl:21-30) ----
+    R A_p, A_rc, A_Gu, A_Gp;
+    {
+        const R rho(row0[0]), ua(row0[FK_VS]), ut(row0[2 * FK_VS]), E(row0[3 * FK_VS]);
+        R p, c;
+        eos_eval<R, DIV_FLAGGED, EOS>(A, rho, ua, ut, E, p, c, f);
+        I.cw[J * 32] = c.v;
+        const R rc = rho * c;
+        acoustic_godunov<R, DIV_FLAGGED>(P.crc[Z1], rc, R(row1[FK_VS]), ua, P.cp[Z1], p, A_Gu, A_Gp, f);
+        A_p = p; A_rc = rc;
+    }
+
+    // ---- chain B, flux at interface i = a-2 (cells a-3, a-2); Godunov states a-3, a-2, a-1 ----
+    R B_Fu, B_Fp;
+    if (RL == 0) {   // acoustic!  src/riemann_schemes.jl:33-43
+        B_Fu = P.Gu[Z2];
+        B_Fp = P.Gp[Z2];
+    } else {         // acoustic_GAD!  src/riemann_schemes.jl:55-104
+        constexpr int LIM = RL - 1;
+        const R u_i(row2[FK_VS]), u_im(row3[FK_VS]), p_i = P.cp[Z2], p_im = P.cp[Z3];
+        const R us_i = P.Gu[Z2], ps_i = P.Gp[Z2];
+        R r_um(1.), r_pm(1.), r_up(1.), r_pp(1.);
+        if (LIM != ARMON_LIMITER_NONE) {   // limiter(r, NoLimiter) == 1 whatever r is (src/limiters.jl:6)
+            r_um = limiter<R, LIM>(D::div(P.Gu[Z1] - u_i, (us_i - u_im) + R(1e-6), f));
+            r_pm = limiter<R, LIM>(D::div(P.Gp[Z1] - p_i, (ps_i - p_im) + R(1e-6), f));
+            r_up = limiter<R, LIM>(D::div(u_im - P.Gu[Z3], (u_i - us_i) + R(1e-6), f));
+            r_pp = limiter<R, LIM>(D::div(p_im - P.Gp[Z3], (p_i - ps_i) + R(1e-6), f));
+        }
+        const R Dm = (R(row3[0]) * dx + R(row2[0]) * dx) * R(0.5);                       // (dm_l + dm_r) / 2, dm = rho dx
+        const R theta = R(0.5) * (R(1.) - ((P.crc[Z3] + P.crc[Z2]) * R(0.5)) * D::div_pos(dt, Dm, f));
+        B_Fu = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
+        B_Fp = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
+    }
+    const R B_FpFu = B_Fp * B_Fu;
+
+    // ---- chain C, Lagrangian update of cell k = a-4 (src/kernels.jl:58-68): interfaces a-4 (left, slot Z0) and a-3
+    //      (right, slot Z3) were committed two steps / one step ago; the cell itself is still in slot Z0 of the cell rings ----
+    R C_disp, C_dxl, C_Lr, C_Lu, C_Lt, C_LE;
+    {
+        C_disp = dt * P.Fu[Z0];
+        C_dxl = dx + dt * (P.Fu[Z3] - P.Fu[Z0]);
+        const R dm = R(row4[0]) * dx;
+        const R dtdm = D::div_pos(dt, dm, f);
+        C_Lr = D::div_pos(dm, C_dxl, f);
+        C_Lu = R(row4[FK_VS]) + dtdm * (P.Fp[Z0] - P.Fp[Z3]);
+        C_LE = R(row4[3 * FK_VS]) + dtdm * (P.FpFu[Z0] - P.FpFu[Z3]);
+        C_Lt = R(row4[2 * FK_VS]);
+    }
+
+    // ---- chain D, advection flux at interface is = a-6 (src/projection_schemes.jl:62-124): cells a-7 (slot Z3), a-6
+    //      (Z2), a-5 (Z1); the per-cell quantities (width ratios, limited slopes, 2 dxl) are formed for cell a-6, those
+    //      of cell a-7 were kept from the previous step (see march_compute) ----
+    R Anr, Anru, Anrt, AnrE;
+    R sr(0.), sru(0.), srt(0.), srE(0.);
+    typename D::Rcp k2;
+    k2.b = 2.0; k2.r = 0.5;
+    {
+        const R d = P.disp[Z2];
+        const bool pos = d.v > 0.0;
+        // rho {ua, ut, E} of the Lagrangian cells a-7, a-6 (cell_update!'s products, formed here: same operands, same bits)
+        const R Lru3 = P.Lr[Z3] * P.Lu[Z3], Lrt3 = P.Lr[Z3] * P.Lt[Z3], LrE3 = P.Lr[Z3] * P.LE[Z3];
+        const R Lru2 = P.Lr[Z2] * P.Lu[Z2], Lrt2 = P.Lr[Z2] * P.Lt[Z2], LrE2 = P.Lr[Z2] * P.LE[Z2];
+        if (PROJ == ARMON_PROJ_EULER_2ND) {
+            const R dxl_m = P.dxl[Z3], dxl_0 = P.dxl[Z2], dxl_p = P.dxl[Z1];
+            const R two_dxl = R(2.) * dxl_0;
+            const R r_m = D::div_pos(two_dxl, dxl_0 + dxl_m, f);
+            const R r_p = D::div_pos(two_dxl, dxl_0 + dxl_p, f);
+            k2 = D::prepare_pos(two_dxl, f);
+            sr = slope_minmod_fused<R>(P.Lr[Z3], P.Lr[Z2], P.Lr[Z1], r_m, r_p);
+            sru = slope_minmod_fused<R>(Lru3, Lru2, P.Lr[Z1] * P.Lu[Z1], r_m, r_p);
+            srt = slope_minmod_fused<R>(Lrt3, Lrt2, P.Lr[Z1] * P.Lt[Z1], r_m, r_p);
+            srE = slope_minmod_fused<R>(LrE3, LrE2, P.Lr[Z1] * P.LE[Z1], r_m, r_p);
+
+            const R dxe = rsel(pos, -(dx - P.disp[Z3]), dx + P.disp[Z1]);
+            typename D::Rcp ksel;
+            ksel.b = pos ? P.S2b.v : k2.b;
+            ksel.r = pos ? P.S2r.v : k2.r;
+            const R lf = D::quot(dxe, ksel, f);
+            Anr = d * (rsel(pos, P.Lr[Z3], P.Lr[Z2]) - rsel(pos, P.Sr, sr) * lf);
+            Anru = d * (rsel(pos, Lru3, Lru2) - rsel(pos, P.Sru, sru) * lf);
+            Anrt = d * (rsel(pos, Lrt3, Lrt2) - rsel(pos, P.Srt, srt) * lf);
+            AnrE = d * (rsel(pos, LrE3, LrE2) - rsel(pos, P.SrE, srE) * lf);
+        } else {
+            Anr = d * rsel(pos, P.Lr[Z3], P.Lr[Z2]);
+            Anru = d * rsel(pos, Lru3, Lru2);
+            Anrt = d * rsel(pos, Lrt3, Lrt2);
+            AnrE = d * rsel(pos, LrE3, LrE2);
+        }
+    }
+
+    // ---- chain E (continues D), projection of cell k = a-7 (src/projection_schemes.jl:23-41) ----
+    if (EMIT == 1) {
+        const R dXr = P.dxl[Z3] * P.Lr[Z3];
+        R t_r = dXr - (Anr - P.Ar);
+        R t_ru = dXr * P.Lu[Z3] - (Anru - P.Aru);
+        R t_rt = dXr * P.Lt[Z3] - (Anrt - P.Art);
+        R t_rE = dXr * P.LE[Z3] - (AnrE - P.ArE);
+        if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
+            const R idx(A.inv_dx);
+            t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
+        } else {
+            t_r = D::quot(t_r, inv_dx, f); t_ru = D::quot(t_ru, inv_dx, f);
+            t_rt = D::quot(t_rt, inv_dx, f); t_rE = D::quot(t_rE, inv_dx, f);
+        }
+        const typename D::Rcp inv_r = D::prepare_pos(t_r, f);
+        const R o_ua = D::quot(t_ru, inv_r, f), o_ut = D::quot(t_rt, inv_r, f), o_E = D::quot(t_rE, inv_r, f);
+        const R c_out(J == 3 ? I.cr[0] : I.cw[(J + 1) * 32]);   // c of cell a-7 (EOS of this sweep)
+        const bool store = ok && J < I.rem;
+        {   // dtCFL accumulators (src/reductions.jl:14-20), branch-free: cells that are not stored do not contribute
+            const unsigned long long ba = (unsigned long long)__double_as_longlong((rabs(o_ua) + c_out).v);
+            const unsigned long long bt = (unsigned long long)__double_as_longlong((rabs(o_ut) + c_out).v);
+            T.amax = (store && ba > T.amax) ? ba : T.amax;
+            T.tmax = (store && bt > T.tmax) ? bt : T.tmax;
+        }
+        if (TR == 1) {
+            double *s = J == 3 ? I.s3 : I.s0 + J;
+            s[0 * 32 * FK_PITCH] = t_r.v;
+            s[1 * 32 * FK_PITCH] = o_ua.v;
+            s[2 * 32 * FK_PITCH] = o_ut.v;
+            s[3 * 32 * FK_PITCH] = o_E.v;
+        } else if (store) {
+            const long long o = I.o_it + J * A.pitch_out;
+            A.out[0][o] = t_r.v;
+            A.out[1][o] = o_ua.v;
+            A.out[2][o] = o_ut.v;
+            A.out[3][o] = o_E.v;
+        }
+    }
+
+    // ---- commit ----
+    P.Ar = Anr; P.Aru = Anru; P.Art = Anrt; P.ArE = AnrE;
+    if (PROJ == ARMON_PROJ_EULER_2ND) {
+        P.Sr = sr; P.Sru = sru; P.Srt = srt; P.SrE = srE;
+        P.S2b = R(k2.b); P.S2r = R(k2.r);
+    }
+    P.cp[Z0] = A_p; P.crc[Z0] = A_rc;
+    P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
+    P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
+    P.disp[Z0] = C_disp; P.dxl[Z0] = C_dxl;
+    P.Lr[Z0] = C_Lr; P.Lu[Z0] = C_Lu; P.Lt[Z0] = C_Lt; P.LE[Z0] = C_LE;
+#undef ZS
+}
+
+__device__ __forceinline__ void fk_pipe_init(PipeF &P)
+{
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cu[j] = 0.; P.cp[j] = 1.; P.crc[j] = 1.; P.cdm[j] = 1.; P.cut[j] = 0.; P.cE[j] = 1.; P.Gu[j] = 0.; P.Gp[j] = 1.;
+        P.Fu[j] = 0.; P.Fp[j] = 1.; P.FpFu[j] = 0.;
+        P.dl[j] = 0.; P.dxl[j] = 1.; P.Lr[j] = 1.; P.Lru[j] = 0.; P.Lrt[j] = 0.; P.LrE[j] = 1.;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { P.T[j][k] = 0.; P.S[j][k] = 0.; P.Adv[j][k] = 0.; }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) P.Q[j][k] = 0.;
+}
+
+// the finite dummies of march_segment (sweep_kernel.cuh): warm-up results are never emitted
+__device__ __forceinline__ void fk_pipe_init(PipeS &P)
+{
+    typedef sd R;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        P.cp[j] = R(1.); P.crc[j] = R(1.);
+        P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
+        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
+    }
+    P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
+    P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
 }
 
 // L2 eviction policies (the encodings of createpolicy.fractional.L2::evict_first / evict_last with fraction 1.0).
@@ -551,11 +776,14 @@ __device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
 
 // CONS = 1: also accumulates the conservation sums of the cells it stores (per-cycle diagnostics fused into the last
 // sweep of a cycle): per thread in march order, per warp by a fixed butterfly, one partial per warp for k_diag_final.
-template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS>
+// MATH = MATH_STRICT: the reference's operation order with correctly rounded divisions (strict_step, section 6.) and the
+// chunk-granular hand-over of out-of-range operands to sweep_fixup_kernel (chunk_end, sweep_async_kernel.cuh).
+template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS, int MATH = MATH_FAST>
 __global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
 sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 {
     static_assert(LAY == LAY_ROWS || STG == STG_TMA, "the tiled layout is staged by TMA only");
+    static_assert(MATH == MATH_FAST || (LAY == LAY_ROWS && CONS == 0 && STG == STG_TMA), "strict arithmetic: row-major layouts, TMA staging");
     extern __shared__ __align__(128) unsigned char fast_smem_raw[];
     // warp index through a shuffle: the compiler then knows it (and every address derived from it: the warp's ring, its
     // barriers, its first column) is warp-uniform and keeps it in uniform registers, which the TMA instructions take
@@ -689,26 +917,26 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
             async_commit();
         }
     };
+    // strict arithmetic: the group consumed by the previous iteration stays in the ring (chain C re-reads ut and E of cell
+    // a-4 from it instead of carrying them in registers), so 8 rows are in flight instead of 12
+    constexpr int LEAD = MATH == MATH_STRICT ? FK_NG - 1 : FK_NG;
     issue_group(0);
     issue_group(1);
     issue_group(2);
-    issue_group(3);
+    if (LEAD == FK_NG) issue_group(3);
 
-    PipeF P;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        P.cu[j] = 0.; P.cp[j] = 1.; P.crc[j] = 1.; P.cdm[j] = 1.; P.cut[j] = 0.; P.cE[j] = 1.; P.Gu[j] = 0.; P.Gp[j] = 1.;
-        P.Fu[j] = 0.; P.Fp[j] = 1.; P.FpFu[j] = 0.;
-        P.dl[j] = 0.; P.dxl[j] = 1.; P.Lr[j] = 1.; P.Lru[j] = 0.; P.Lrt[j] = 0.; P.LrE[j] = 1.;
+    typename std::conditional<MATH == MATH_STRICT, PipeS, PipeF>::type P;
+    fk_pipe_init(P);
+    // strict arithmetic: range bookkeeping of the branch-free divisions, evaluated once per chunk of FK_K emitted cells
+    typename Div<sd, DIV_FLAGGED>::Rcp inv_dx;
+    inv_dx.b = A.dx; inv_dx.r = A.inv_dx;
+    ChunkFix C;
+    C.tot_a = 0ULL; C.tot_t = 0ULL; C.taint = 0; C.always = false;
+    if (MATH == MATH_STRICT) {
+        inv_dx = Div<sd, DIV_FLAGGED>::prepare(sd(A.dx), T.flag);
+        range_check_dividend(dt, T.flag);
+        C.always = T.flag.bad();
     }
-#pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) { P.T[j][k] = 0.; P.S[j][k] = 0.; P.Adv[j][k] = 0.; }
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) P.Q[j][k] = 0.;
 
     const double *ring = &S.ring[0][0][0][0] + (LAY == LAY_TILED ? (lane >> 3) * 32 + (lane & 7) : lane);
     double *cring = &S.cring[0][lane];
@@ -716,19 +944,38 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     // tiled transposed stores: output row w + g = band (w0 + g) / 4 + lane / 4, row lane & 3 of its tiles
     const long long q_lane = (((w0 + A.g) >> 2) + (lane >> 2)) * (4 * A.pitch_out) + (lane & 3) * 8;
     FastIter I;
-    I.q_off = 0; I.qok = false;
+    I.q_off = 0; I.qok = false; I.row_mask = 0xfu;
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
-#define FK_STEP(Jv, EMITv, OK) fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS, LAY>(A, T, P, I, dt, OK);
+#define FK_STEP(Jv, EMITv, OK)                                                                              \
+    if constexpr (MATH == MATH_STRICT) strict_step<RL, PROJ, EOS, Jv, TR, EMITv>(A, T, P, I, sd(dt), inv_dx, OK);  \
+    else fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS, LAY>(A, T, P, I, dt, OK);
 #define FK_BEGIN(it)                                                                                        \
     {                                                                                                       \
         const int p_ = (it) & 1;                                                                            \
         I.gb0 = ring + ((it) & (FK_NG - 1)) * FK_GS;                                                        \
+        I.gbm = ring + (((it) + FK_NG - 1) & (FK_NG - 1)) * FK_GS;                                          \
         I.cw = cring + p_ * 4 * 32;                                                                         \
         I.cr = cring + (p_ ^ 1) * 4 * 32;                                                                   \
+        if (MATH == MATH_STRICT) {   /* rows a_begin + 4 it + J inside [-g, nm + g): bits J of the mask */          \
+            const long long lo_ = -(long long)A.g - (a_begin + 4 * (it)), hi_ = A.nm + A.g - 1 - (a_begin + 4 * (it)); \
+            const unsigned m_hi_ = hi_ >= 3 ? 0xfu : hi_ < 0 ? 0u : ((2u << (int)hi_) - 1u);                \
+            const unsigned m_lo_ = lo_ <= 0 ? 0xfu : lo_ > 3 ? 0u : ((0xfu << (int)lo_) & 0xfu);            \
+            I.row_mask = m_hi_ & m_lo_;                                                                     \
+        }                                                                                                   \
         if (STG == STG_TMA) {                                                                               \
             if (!landed) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
         } else { async_wait<3>(); __syncwarp(); }                                                           \
+        if (MATH == MATH_STRICT && I.row_mask != 0xfu) {                                                    \
+            /* rows outside the array were zero-filled by the copy engine: give them a benign state (rho = 1e4, */ \
+            /* E = 1: in range for both EOS) before anything reads them; they only feed cells never stored */ \
+            double *g_ = const_cast<double *>(I.gb0);                                                       \
+            _Pragma("unroll")                                                                               \
+            for (int j_ = 0; j_ < 4; j_++)                                                                  \
+                if (!((I.row_mask >> j_) & 1u)) { g_[j_ * 32] = 1e4; g_[j_ * 32 + 3 * FK_VS] = 1.0; }       \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* ordered before the slot's next bulk copy */ \
+            __syncwarp();                                                                                   \
+        }                                                                                                   \
     }
     /* early look at the barrier of the next iteration's group */
 #define FK_PEEK(it)                                                                                         \
@@ -736,7 +983,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 #define FK_END(it)                                                                                          \
     {                                                                                                       \
         __syncwarp();   /* every lane has read the last row of group it: refill its slot */                 \
-        issue_group((it) + 4);                                                                              \
+        issue_group((it) + LEAD);                                                                           \
     }
 
     // warm-up: steps 0 .. 7 fill the head of the dependency cone of the first output, nothing is emitted
@@ -786,6 +1033,12 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         FK_PEEK(it)
         FK_STEP(2, 1, ok012)
         if (TR == 1 && LAY == LAY_ROWS && k3 == 0 && live) fast_flush(A, S.stage, w0, m0 + (4 * it - 8 - FK_K), m_lo, m1);
+        if (MATH == MATH_STRICT && k3 == 0 && live) {
+            // the chunk [mb, mb + FK_K) is complete; an out-of-range operand met since the last check reaches cells
+            // emitted at most 11 steps later, i.e. chunks k .. k+2 = the FIX_CHUNKS * SWEEP_CHUNK rows of a work-list entry
+            const long long mb = m0 + (4 * it - 8 - FK_K);
+            chunk_end<DIV_FLAGGED>(A, T, C, mb < 0 ? 0 : mb, w);
+        }
         FK_STEP(3, 1, ok3)
         FK_END(it)
     }
@@ -795,7 +1048,8 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 #undef FK_END
     if (STG != STG_TMA) async_wait<0>();
 
-    unsigned long long am = T.valid ? T.amax : 0ULL, tm = T.valid ? T.tmax : 0ULL;
+    unsigned long long am = T.valid ? (MATH == MATH_STRICT ? C.tot_a : T.amax) : 0ULL;
+    unsigned long long tm = T.valid ? (MATH == MATH_STRICT ? C.tot_t : T.tmax) : 0ULL;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long oa = __shfl_xor_sync(0xffffffffu, am, off);

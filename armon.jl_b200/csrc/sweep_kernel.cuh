@@ -195,7 +195,7 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
             r_pp = limiter<R, LIM>(D::div(p_im - P.Gp[S2], (p_i - ps_i) + R(1e-6), f));
         }
         const R Dm = (P.cdm[S2] + P.cdm[S1]) * R(0.5);                                   // (dm_l + dm_r) / 2
-        const R theta = R(0.5) * (R(1.) - ((P.crc[S2] + P.crc[S1]) * R(0.5)) * D::div(dt, Dm, f));
+        const R theta = R(0.5) * (R(1.) - ((P.crc[S2] + P.crc[S1]) * R(0.5)) * D::div_pos(dt, Dm, f));
         P.Fu[S1] = us_i + theta * (r_up * (u_i - us_i) - r_um * (us_i - u_im));
         P.Fp[S1] = ps_i + theta * (r_pp * (p_i - ps_i) - r_pm * (ps_i - p_im));
     }
@@ -206,8 +206,8 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
     {
         const R dxl = dx + dt * (P.Fu[S1] - P.Fu[S2]);
         const R dm = P.cdm[S2];
-        const R dtdm = D::div(dt, dm, f);
-        const R Lr = D::div(dm, dxl, f);
+        const R dtdm = D::div_pos(dt, dm, f);
+        const R Lr = D::div_pos(dm, dxl, f);
         const R Lu = P.cu[S2] + dtdm * (P.Fp[S2] - P.Fp[S1]);
         const R LE = P.cE[S2] + dtdm * (P.FpFu[S2] - P.FpFu[S1]);
         const R Lt = P.cut[S2];
@@ -228,9 +228,9 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
         if (PROJ == ARMON_PROJ_EULER_2ND) {
             const R dxl_m = P.dxl[S0], dxl_0 = P.dxl[S3], dxl_p = P.dxl[S2];
             const R two_dxl = R(2.) * dxl_0;
-            const R r_m = D::div(two_dxl, dxl_0 + dxl_m, f);
-            const R r_p = D::div(two_dxl, dxl_0 + dxl_p, f);
-            const typename D::Rcp k2 = D::prepare(two_dxl, f);
+            const R r_m = D::div_pos(two_dxl, dxl_0 + dxl_m, f);
+            const R r_p = D::div_pos(two_dxl, dxl_0 + dxl_p, f);
+            const typename D::Rcp k2 = D::prepare_pos(two_dxl, f);
             const R sr = slope_minmod_fused<R>(P.Lr[S0], P.Lr[S3], P.Lr[S2], r_m, r_p);
             const R sru = slope_minmod_fused<R>(P.Lru[S0], P.Lru[S3], P.Lru[S2], r_m, r_p);
             const R srt = slope_minmod_fused<R>(P.Lrt[S0], P.Lrt[S3], P.Lrt[S2], r_m, r_p);
@@ -273,7 +273,7 @@ __device__ __forceinline__ void march_compute(const SweepArgs &A, SweepThread &T
             t_r = D::quot(t_r, inv_dx, f); t_ru = D::quot(t_ru, inv_dx, f);
             t_rt = D::quot(t_rt, inv_dx, f); t_rE = D::quot(t_rE, inv_dx, f);
         }
-        const typename D::Rcp inv_r = D::prepare(t_r, f);
+        const typename D::Rcp inv_r = D::prepare_pos(t_r, f);
         const R o_ua = D::quot(t_ru, inv_r, f), o_ut = D::quot(t_rt, inv_r, f), o_E = D::quot(t_rE, inv_r, f);
         const long long m = a - 4;
         const bool store = T.valid && m < m1;
