@@ -110,6 +110,7 @@ SIGNATURES = {
     "armon_solver_elapsed_ms": [_VP, C.POINTER(C.c_float)],
     "armon_solver_sweep_launches": [_VP, C.POINTER(C.c_uint64)],
     "armon_solver_tiled": [_VP, C.POINTER(C.c_int32)],
+    "armon_solver_strict_chains": [_VP, C.POINTER(C.c_int32)],
     "armon_solver_profile": [_VP, C.c_int],
     "armon_solver_sweep_time_ms": [_VP, PD, C.POINTER(C.c_uint64)],
     "armon_solver_diagnostics": [_VP, C.c_int32],

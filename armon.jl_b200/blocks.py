@@ -240,6 +240,13 @@ class BlockGrid:
         check(self.lib.armon_solver_tiled(self.blocks[0].solver, C.byref(tiled)), "armon_solver_tiled")
         return tiled.value
 
+    def strict_kernel_is_chains(self):
+        """1 when the strict (bit-exact) sweeps run on the four-chain schedule of the fast kernel
+        (armon_solver_strict_chains), 0 for the unskewed cp.async kernel or another arithmetic mode."""
+        chains = C.c_int32(0)
+        check(self.lib.armon_solver_strict_chains(self.blocks[0].solver, C.byref(chains)), "armon_solver_strict_chains")
+        return chains.value
+
     def reset(self):                                # reset!(grid, params), src/blocking/block_grid.jl:555-561
         self.global_dt.reset(self.params)
         self.state.reset()

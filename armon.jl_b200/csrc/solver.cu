@@ -1266,7 +1266,7 @@ void group_free_common(armon_group *G)
 }
 
 #ifndef ARMON_STRICT_CHAINS_DEFAULT
-#define ARMON_STRICT_CHAINS_DEFAULT false
+#define ARMON_STRICT_CHAINS_DEFAULT true
 #endif
 
 // Select the marching kernels of a solver from its descriptor.
@@ -1614,6 +1614,14 @@ int armon_solver_tiled(armon_solver *s, int32_t *tiled)
     if (int rc = solver_check(s, false, false)) return rc;
     ARMON_CHECK_ARG(tiled != nullptr, "null result");
     *tiled = s->group->tiled;
+    return ARMON_OK;
+}
+
+int armon_solver_strict_chains(armon_solver *s, int32_t *chains)
+{
+    if (int rc = solver_check(s, false, false)) return rc;
+    ARMON_CHECK_ARG(chains != nullptr, "null result");
+    *chains = s->use_strict4 ? 1 : 0;
     return ARMON_OK;
 }
 

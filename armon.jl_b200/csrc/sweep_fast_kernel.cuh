@@ -402,6 +402,14 @@ __device__ __forceinline__ void fast_step(const SweepArgs &A, SweepThread &T, Pi
 // Rows outside the array (the 4 virtual cells before the first segment, the rows the last segment consumes past the
 // last ghost row) are zero-filled by the copy engine; they only feed cells that are never stored, but a zero density
 // would raise the thread's range flag and send real chunks to the fix-up: chain A replaces them by a benign state.
+// pos ? a : b as a bit blend with a precomputed all-ones / all-zeros mask: one LOP3 per 32-bit half, whereas the
+// compiler lowers the ten upwind selections of a step to pairs of (predicated) register moves at this register pressure
+__device__ __forceinline__ sd sblend(unsigned long long m, sd a, sd b)
+{
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(a.v), ub = (unsigned long long)__double_as_longlong(b.v);
+    return sd(__longlong_as_double((long long)((ua & m) | (ub & ~m))));
+}
+
 struct PipeS {
     sd cp[4], crc[4];                                       // cells a-1 .. a-3: p, rho c (what the EOS computed; rho, ua, ut
                                                             // and E of the cells a-1 .. a-4 are re-read from the staging
@@ -491,7 +499,7 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
     k2.b = 2.0; k2.r = 0.5;
     {
         const R d = P.disp[Z2];
-        const bool pos = d.v > 0.0;
+        const unsigned long long pm = d.v > 0.0 ? ~0ULL : 0ULL;   // disp > 0: the upwind cell is a-7
         // rho {ua, ut, E} of the Lagrangian cells a-7, a-6 (cell_update!'s products, formed here: same operands, same bits)
         const R Lru3 = P.Lr[Z3] * P.Lu[Z3], Lrt3 = P.Lr[Z3] * P.Lt[Z3], LrE3 = P.Lr[Z3] * P.LE[Z3];
         const R Lru2 = P.Lr[Z2] * P.Lu[Z2], Lrt2 = P.Lr[Z2] * P.Lt[Z2], LrE2 = P.Lr[Z2] * P.LE[Z2];
@@ -506,20 +514,20 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
             srt = slope_minmod_fused<R>(Lrt3, Lrt2, P.Lr[Z1] * P.Lt[Z1], r_m, r_p);
             srE = slope_minmod_fused<R>(LrE3, LrE2, P.Lr[Z1] * P.LE[Z1], r_m, r_p);
 
-            const R dxe = rsel(pos, -(dx - P.disp[Z3]), dx + P.disp[Z1]);
+            const R dxe = sblend(pm, -(dx - P.disp[Z3]), dx + P.disp[Z1]);
             typename D::Rcp ksel;
-            ksel.b = pos ? P.S2b.v : k2.b;
-            ksel.r = pos ? P.S2r.v : k2.r;
+            ksel.b = sblend(pm, P.S2b, R(k2.b)).v;
+            ksel.r = sblend(pm, P.S2r, R(k2.r)).v;
             const R lf = D::quot(dxe, ksel, f);
-            Anr = d * (rsel(pos, P.Lr[Z3], P.Lr[Z2]) - rsel(pos, P.Sr, sr) * lf);
-            Anru = d * (rsel(pos, Lru3, Lru2) - rsel(pos, P.Sru, sru) * lf);
-            Anrt = d * (rsel(pos, Lrt3, Lrt2) - rsel(pos, P.Srt, srt) * lf);
-            AnrE = d * (rsel(pos, LrE3, LrE2) - rsel(pos, P.SrE, srE) * lf);
+            Anr = d * (sblend(pm, P.Lr[Z3], P.Lr[Z2]) - sblend(pm, P.Sr, sr) * lf);
+            Anru = d * (sblend(pm, Lru3, Lru2) - sblend(pm, P.Sru, sru) * lf);
+            Anrt = d * (sblend(pm, Lrt3, Lrt2) - sblend(pm, P.Srt, srt) * lf);
+            AnrE = d * (sblend(pm, LrE3, LrE2) - sblend(pm, P.SrE, srE) * lf);
         } else {
-            Anr = d * rsel(pos, P.Lr[Z3], P.Lr[Z2]);
-            Anru = d * rsel(pos, Lru3, Lru2);
-            Anrt = d * rsel(pos, Lrt3, Lrt2);
-            AnrE = d * rsel(pos, LrE3, LrE2);
+            Anr = d * sblend(pm, P.Lr[Z3], P.Lr[Z2]);
+            Anru = d * sblend(pm, Lru3, Lru2);
+            Anrt = d * sblend(pm, Lrt3, Lrt2);
+            AnrE = d * sblend(pm, LrE3, LrE2);
         }
     }
 

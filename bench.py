@@ -308,6 +308,8 @@ class GpuJob:
         # which layout the fused path actually ran in (sweep_fast_kernel.cuh 5.): asked from the library, not assumed
         if self.grid.fused_layout_is_tiled() == 1:
             variant, kname = "tiled", "sweep_fast_kernel<STG_TMA, LAY_TILED"
+        elif self.math == "strict" and self.grid.strict_kernel_is_chains() == 1 and self.params.N[0] % 2 == 0 and self.params.N[1] % 2 == 0:
+            variant, kname = "chains", "sweep_fast_kernel<STG_TMA, MATH_STRICT"
         key = f"{variant}_{self.math}_{'biz' if biz else 'pg'}"
         traffic = load_profile_json("sweep_traffic.json") or {}
         t = traffic.get(key)

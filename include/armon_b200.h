@@ -275,6 +275,11 @@ int armon_solver_sweep_launches(armon_solver *solver, uint64_t *count);
  * ARMON_B200_TILED=0 disables), 0 when it runs the row-major / transposed pair, -1 before the first cycle decided it.
  * The arrays the caller sees (armon_solver_bind, after armon_solver_finalize) are always in the canonical layout. */
 int armon_solver_tiled(armon_solver *solver, int32_t *tiled);
+/* Kernel of the bit-exact arithmetic mode (no reference counterpart): *chains = 1 when the solver's strict sweeps run
+ * on the four-chain schedule of the fast kernel (sweep_fast_kernel<..., MATH_STRICT>, TMA staging; the default for
+ * math_mode strict, ARMON_B200_STRICT=async turns it off), 0 when they run the unskewed cp.async kernel or the solver
+ * is not in strict mode.  Same bits either way; informational (bench.py names the kernel it timed). */
+int armon_solver_strict_chains(armon_solver *solver, int32_t *chains);
 
 /* Per-cycle diagnostics without a host round trip: the reference's `silent <= 1` log line (src/solver.jl:359-371:
  * wait + conservation_vars + print after every cycle).  While enabled, every cycle enqueues a fixed-tree reduction of

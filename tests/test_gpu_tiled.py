@@ -155,3 +155,44 @@ def test_tiled_layout_cycles_past_the_end_and_graph_replay():
         s0.data.close(); s1.data.close(); g2.close()
     finally:
         del os.environ["ARMON_B200_TILED"]
+
+
+def run_strict(params, kernel):
+    """armon(params) in math_mode strict with the sweep kernel forced (ARMON_B200_STRICT = chains | async)."""
+    old = os.environ.get("ARMON_B200_STRICT")
+    os.environ["ARMON_B200_STRICT"] = kernel
+    try:
+        params.return_data = True
+        stats = armon.armon(params)
+        grid = stats.data
+        assert grid.strict_kernel_is_chains() == (1 if kernel == "chains" else 0)   # the kernel asked for is the kernel that ran
+        out = {v: grid.real(v).copy() for v in VARS}
+        grid.close()
+    finally:
+        if old is None:
+            del os.environ["ARMON_B200_STRICT"]
+        else:
+            os.environ["ARMON_B200_STRICT"] = old
+    return stats, out
+
+
+@pytest.mark.parametrize("test,N,scheme,limiter,projection,splitting,cycles,segment", CASES)
+def test_strict_chains_kernel_gives_the_same_bits(test, N, scheme, limiter, projection, splitting, cycles, segment):
+    """The two kernels of the bit-exact mode -- the strict arithmetic on the four-chain schedule of the fast kernel
+    (sweep_fast_kernel<..., MATH_STRICT>, the default) and the unskewed cp.async kernel -- and the strict CPU oracle
+    agree bit for bit: every test case, scheme, limiter, projection and splitting, forced march segments, extents from
+    one band of rows to 1024 x 520 (non-power-of-two cell sizes included: the x / dx division path)."""
+    kw = dict(N=N, maxcycle=cycles, scheme=scheme, riemann_limiter=limiter, projection=projection,
+              axis_splitting=splitting, march_segment=segment, math_mode="strict")
+    s_c, chains = run_strict(reference_params(test, **kw), "chains")
+    s_a, unskewed = run_strict(reference_params(test, **kw), "async")
+    assert (s_c.cycles, s_c.last_dt, s_c.final_time) == (s_a.cycles, s_a.last_dt, s_a.final_time)
+    for v in VARS:
+        assert_same(chains[v], unskewed[v], f"{test} {N} {v}: chains vs async")
+    okw = {k: v for k, v in kw.items() if k not in ("march_segment", "math_mode")}
+    orc = OracleSolver(reference_params(test, **okw), "strict", nthreads=os.cpu_count() or 1)
+    _, dt, ncyc, err = orc.time_loop()
+    assert err == 0 and (ncyc, dt) == (s_c.cycles, s_c.last_dt)
+    for v in ("rho", "u", "v", "E", "p"):
+        assert_same(chains[v], orc.real(v), f"{test} {N} {v}: chains vs oracle")
+    orc.close()
