@@ -242,7 +242,7 @@ class BlockGrid:
 
     def strict_kernel_is_chains(self):
         """1 when the strict (bit-exact) sweeps run on the four-chain schedule of the fast kernel
-        (armon_solver_strict_chains), 0 for the unskewed cp.async kernel or another arithmetic mode."""
+        (armon_solver_strict_chains), 0 for the register-prefetch kernel or another arithmetic mode."""
         chains = C.c_int32(0)
         check(self.lib.armon_solver_strict_chains(self.blocks[0].solver, C.byref(chains)), "armon_solver_strict_chains")
         return chains.value

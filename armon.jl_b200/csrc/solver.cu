@@ -361,10 +361,7 @@ struct armon_solver {
     cudaEvent_t       ev_edge = nullptr;                       // edge segments done
     uint64_t          sweep_launches = 0;
     sweep_fn_t        kernel = nullptr;                        // register-prefetch marching kernel (always available)
-    sweep_fn_t        staged_kernel[2] = {nullptr, nullptr};   // shared-memory staged marching kernel, [transposed output]
-    bool              use_staged = false;
-    size_t            staged_smem = 0;         // dynamic shared memory per CTA of the staged kernel
-    sweep_fixup_fn_t  fixup_kernel = nullptr;  // IEEE fix-up of the strict staged kernel
+    sweep_fixup_fn_t  fixup_kernel = nullptr;  // IEEE fix-up of the strict mode's staged kernel (strict4_kernel)
     // fast-mode marching kernels (sweep_fast_kernel.cuh), [staging variant][transposed output]; `fast_stg` is the
     // staging used for even pitches (STG_TMA or STG_CPA16), odd pitches always take STG_CPA8
     sweep_fast_fn_t   fast_kernel[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -372,7 +369,7 @@ struct armon_solver {
     int               fast_stg = STG_TMA;
     sweep_fast_fn_t   fast_cons_kernel[2] = {nullptr, nullptr};   // TMA staging + conservation sums, [transposed output]
     // strict arithmetic on the fast kernel's schedule (sweep_fast_kernel.cuh 6.), [transposed output]; even pitches
-    sweep_fast_fn_t   strict4_kernel[2] = {nullptr, nullptr};
+    sweep_fast_fn_t   strict4_kernel[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [cell size is a power of two][transposed output]
     bool              use_strict4 = false;
     // per-cycle diagnostics: this block's region of the group's partial-sum scratch, and whether the last sweep of the
     // cycle being enqueued filled it itself (fused) or k_diag_rows has to
@@ -579,11 +576,10 @@ int pick_segment(const armon_solver *s, long long nm, long long nw)
         }
         return best;
     }
-    // as long as possible (the warm-up rows of every segment are redundant work) while keeping >= 6 waves of CTAs; the
-    // staged kernels run 8 warps per SM whatever their CTA size
-    const bool staged_ok = s->use_staged && ((nw + 2 * s->d.dims.g) % 2) == 0;
-    const long long cols_per_cta = staged_ok ? ASYNC_TPB : SWEEP_TPB;
-    const long long ctas_per_sm = staged_ok ? 256 / ASYNC_TPB : 2;
+    // register-prefetch kernels: as long as possible (the warm-up rows of every segment are redundant work) while
+    // keeping >= 6 waves of CTAs
+    const long long cols_per_cta = SWEEP_TPB;
+    const long long ctas_per_sm = 2;
     const long long ncol = (nw + cols_per_cta - 1) / cols_per_cta;
     const long long want = 6LL * ctas_per_sm * s->ctx->sm_count;
     const int cands[] = {2048, 1024, 512, 256, 128, 64, 32, 16};
@@ -686,7 +682,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     // (the fast kernels cut their segments 4 cells earlier -- 64-byte aligned transposed stores -- so their last
     // segment is never shorter than 5 cells)
     // strict arithmetic on the fast kernel's schedule: TMA staging needs 16-byte aligned rows (even pitch)
-    const bool strict4_launch = s->use_strict4 && (A.pitch_in % 2) == 0 && s->strict4_kernel[A.transpose_out ? 1 : 0] != nullptr;
+    const bool strict4_launch = s->use_strict4 && (A.pitch_in % 2) == 0;
     const bool short_tail = !(s->use_fast || strict4_launch) && A.nm - (nseg - 1) * A.seg < A.g;
     const long long n_interior = nseg - 2 - (short_tail ? 1 : 0);
     const bool overlap = has_nb && n_interior >= 1 && s->overlap;
@@ -721,8 +717,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
     A.cons_m = cons ? s->cons_m : nullptr;
     A.cons_e = cons ? s->cons_e : nullptr;
     s->cons_done = cons;
-    const bool staged_launch = !fast_launch && s->use_staged && (A.pitch_in % 2) == 0;
-    const long long cols_per_cta = (staged_launch || fast_launch) ? ASYNC_TPB : SWEEP_TPB;
+    const long long cols_per_cta = fast_launch ? ASYNC_TPB : SWEEP_TPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (s->profile) {
         if (s->prof_used + 2 > s->prof_events.size()) {
@@ -737,7 +732,7 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         s->prof_used += 2;
         ARMON_CUDA(cudaEventRecord(ev0, s->ctx->stream));
     }
-    const bool with_fixup = (staged_launch || strict4_launch) && s->fixup_kernel;
+    const bool with_fixup = strict4_launch && s->fixup_kernel;
     FixupArgs F;
     F.count = s->fix_count ? s->fix_count + (s->sweep_index & 1) : nullptr;
     F.count_next = s->fix_count ? s->fix_count + ((s->sweep_index + 1) & 1) : nullptr;
@@ -753,12 +748,10 @@ int launch_sweep(armon_solver *s, int axis, double dt_factor, int acc_slot, int 
         // (tiled: the threads are shifted by the g ghost columns, sweep_fast_kernel.cuh 5.)
         const dim3 grid((unsigned)((A.nw + (tiled ? D.g : 0) + cols_per_cta - 1) / cols_per_cta), (unsigned)ny, 1);
         if (fast_launch)
-            (strict4_launch ? s->strict4_kernel[tr]
+            (strict4_launch ? s->strict4_kernel[A.dx_pow2 ? 1 : 0][tr]
              : tiled ? (cons ? s->fast_tiled_cons_kernel[tr] : s->fast_tiled_kernel[tr])
                      : (cons ? s->fast_cons_kernel[tr] : s->fast_kernel[stg][tr]))
                 <<<grid, ASYNC_TPB, ASYNC_TPB / 32 * sizeof(FastWarpShared), st>>>(A, maps);
-        else if (staged_launch)
-            s->staged_kernel[A.transpose_out ? 1 : 0]<<<grid, ASYNC_TPB, s->staged_smem, st>>>(A);
         else
             s->kernel<<<grid, SWEEP_TPB, 0, st>>>(A);
         ARMON_LAUNCH_CHECK(s->ctx);
@@ -1265,10 +1258,6 @@ void group_free_common(armon_group *G)
     if (G->agree) cudaFree(G->agree);
 }
 
-#ifndef ARMON_STRICT_CHAINS_DEFAULT
-#define ARMON_STRICT_CHAINS_DEFAULT true
-#endif
-
 // Select the marching kernels of a solver from its descriptor.
 int select_kernels(armon_solver *s)
 {
@@ -1288,8 +1277,7 @@ int select_kernels(armon_solver *s)
     }
     // kernel_variant / ARMON_B200_KERNEL: auto | single | async | async2 | tma (include/armon_b200.h,
     // ARMON_KERNEL_*).  auto: fast mode -> the explicit-arithmetic kernel with TMA staging (cp.async for odd pitches);
-    // strict mode -> the unskewed cp.async kernel (it is register-bound either way and measures the same or better
-    // without the skew) + IEEE fix-up; ieee -> `single`.
+    // strict mode -> `async`: the strict arithmetic on the fast kernel's schedule + IEEE fix-up (see below); ieee -> `single`.
     int variant = desc->kernel_variant;
     if (const char *env = getenv("ARMON_B200_KERNEL")) {
         const std::string e(env);
@@ -1349,32 +1337,19 @@ int select_kernels(armon_solver *s)
         }
         s->tiled_ok = tiled;
     }
+    // math_mode strict, variant async (the default): the strict arithmetic on the four-chain schedule of the fast kernel
+    // (sweep_fast_kernel<..., MATH_STRICT>, TMA staging: even pitches; odd pitches take s->kernel) + the IEEE fix-up of
+    // the chunks whose division operands left the proven range.  ARMON_B200_STRICT=single keeps the register-prefetch
+    // kernel everywhere (comparison runs, tests).
     if (variant == ARMON_KERNEL_ASYNC && desc->math_mode == ARMON_MATH_STRICT) {
-        bool ok = true;
-        s->staged_smem = ASYNC_TPB / 32 * sizeof(AsyncWarpShared);
-        for (int tr = 0; tr < 2; tr++) {
-            s->staged_kernel[tr] = biz ? sweep_async_table_strict_biz(rl, desc->projection, tr)
-                                       : sweep_async_table_strict_pg(rl, desc->projection, tr);
-            ok = ok && s->staged_kernel[tr] != nullptr;
-            if (s->staged_kernel[tr]) {
-                ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->staged_smem));
-                ARMON_CUDA(cudaFuncSetAttribute((const void *)s->staged_kernel[tr],
-                                                cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
-            }
-        }
-        s->use_staged = ok;
-    }
-    // ARMON_B200_STRICT=chains: the strict arithmetic on the four-chain schedule of the fast kernel (TMA staging);
-    // =async: the unskewed cp.async kernel
-    if (s->use_staged && desc->math_mode == ARMON_MATH_STRICT) {
         const char *sk = getenv("ARMON_B200_STRICT");
-        const bool want = sk ? std::string(sk) == "chains" : ARMON_STRICT_CHAINS_DEFAULT;
+        const bool want = !(sk && std::string(sk) == "single");
         bool ok = want;
-        for (int tr = 0; tr < 2 && want; tr++) {
-            sweep_fast_fn_t fn = biz ? sweep_fast_table_strict_biz(rl, desc->projection, tr) : sweep_fast_table_strict_pg(rl, desc->projection, tr);
-            s->strict4_kernel[tr] = fn;
+        for (int k = 0; k < 4 && want; k++) {
+            const int dxp = k >> 1, tr = k & 1;
+            sweep_fast_fn_t fn = dxp ? (biz ? sweep_fast_table_strict_dxp_biz(rl, desc->projection, tr) : sweep_fast_table_strict_dxp_pg(rl, desc->projection, tr))
+                                     : (biz ? sweep_fast_table_strict_biz(rl, desc->projection, tr) : sweep_fast_table_strict_pg(rl, desc->projection, tr));
+            s->strict4_kernel[dxp][tr] = fn;
             ok = ok && fn != nullptr;
             if (!fn) continue;
             ARMON_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1384,7 +1359,7 @@ int select_kernels(armon_solver *s)
         }
         s->use_strict4 = ok;
     }
-    if (s->use_staged && desc->math_mode == ARMON_MATH_STRICT) {
+    if (s->use_strict4) {
         s->fixup_kernel = biz ? sweep_fixup_table_biz(rl, desc->projection) : sweep_fixup_table_pg(rl, desc->projection);
         // work list of the IEEE fix-up: one entry per (column, chunk of 8 rows) at most; capped at 32 MB, an overflow (a
         // domain full of out-of-range values) raises ARMON_ERR_RANGE

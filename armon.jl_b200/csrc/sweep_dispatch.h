@@ -3,8 +3,8 @@
 //
 // Families on the product path:
 //   sweep_kernel        (register prefetch)  : every math mode; the fallback for odd input pitches and math_mode ieee
-//   sweep_async_kernel  (cp.async staging)   : math_mode strict (bit-exact), + sweep_fixup_kernel
-//   sweep_fast_kernel   (TMA / cp.async)     : math_mode fast, explicit arithmetic, 4 chains per step
+//   sweep_fast_kernel   (TMA / cp.async)     : four chains per step; math_mode fast (explicit arithmetic, band-tiled layout)
+//                                              and math_mode strict (MATH_STRICT, bit-exact, + sweep_fixup_kernel)
 #pragma once
 #include "sweep_kernel.cuh"
 #include "sweep_fixup_kernel.cuh"
@@ -34,7 +34,7 @@ sweep_fn_t sweep_table_fast_biz(int rl, int proj);
         return table[rl][proj];                                                             \
     }
 
-// IEEE fix-up kernels of the strict cp.async sweep
+// IEEE fix-up kernels of the strict sweep (sweep_fast_kernel<..., MATH_STRICT>)
 sweep_fixup_fn_t sweep_fixup_table_pg(int rl, int proj);
 sweep_fixup_fn_t sweep_fixup_table_biz(int rl, int proj);
 
@@ -49,25 +49,6 @@ sweep_fixup_fn_t sweep_fixup_table_biz(int rl, int proj);
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1) return nullptr;                       \
         return table[rl][proj];                                                             \
-    }
-
-// cp.async-staged marching kernels (sweep_async_kernel.cuh); tr = 1: transposed output.
-sweep_fn_t sweep_async_table_strict_pg(int rl, int proj, int tr);
-sweep_fn_t sweep_async_table_strict_biz(int rl, int proj, int tr);
-
-#define ARMON_ASYNC_ROW(R, DIV, RLV, EOS)                                                    \
-    {{sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 0>, sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER, EOS, 1>}, \
-     {sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 0>, sweep_async_kernel<R, DIV, RLV, ARMON_PROJ_EULER_2ND, EOS, 1>}}
-
-#define ARMON_DEFINE_ASYNC_TABLE(NAME, R, DIV, EOS)                                          \
-    sweep_fn_t NAME(int rl, int proj, int tr)                                               \
-    {                                                                                       \
-        static const sweep_fn_t table[4][2][2] = {                                          \
-            ARMON_ASYNC_ROW(R, DIV, 0, EOS), ARMON_ASYNC_ROW(R, DIV, 1, EOS),               \
-            ARMON_ASYNC_ROW(R, DIV, 2, EOS), ARMON_ASYNC_ROW(R, DIV, 3, EOS),               \
-        };                                                                                  \
-        if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
-        return table[rl][proj][tr];                                                         \
     }
 
 // Fast-mode marching kernels (sweep_fast_kernel.cuh): explicit arithmetic, staged by TMA / cp.async; tr = 1: transposed
@@ -90,21 +71,24 @@ sweep_fast_fn_t sweep_fast_table_tiled_cons_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_tiled_cons_biz(int rl, int proj, int tr);
 
 // strict arithmetic on the schedule of the fast kernel (MATH_STRICT: TMA staging, row-major layouts, four chains per step)
+// (_dxp: cell size a power of two -- x / dx is a multiplication, decided at compile time)
 sweep_fast_fn_t sweep_fast_table_strict_pg(int rl, int proj, int tr);
 sweep_fast_fn_t sweep_fast_table_strict_biz(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_strict_dxp_pg(int rl, int proj, int tr);
+sweep_fast_fn_t sweep_fast_table_strict_dxp_biz(int rl, int proj, int tr);
 
-#define ARMON_FAST_ROW_M(STG, RLV, EOS, CONS, LAY, MATH)                                     \
-    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS, LAY, MATH>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS, LAY, MATH>}, \
-     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS, LAY, MATH>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS, LAY, MATH>}}
+#define ARMON_FAST_ROW_M(STG, RLV, EOS, CONS, LAY, MATH, DXP)                                \
+    {{sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 0, CONS, LAY, MATH, DXP>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER, EOS, 1, CONS, LAY, MATH, DXP>}, \
+     {sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 0, CONS, LAY, MATH, DXP>, sweep_fast_kernel<STG, RLV, ARMON_PROJ_EULER_2ND, EOS, 1, CONS, LAY, MATH, DXP>}}
 
-#define ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH)                           \
+#define ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH, DXP)                      \
     sweep_fast_fn_t NAME(int rl, int proj, int tr)                                          \
     {                                                                                       \
         static const sweep_fast_fn_t table[4][2][2] = {                                     \
-            ARMON_FAST_ROW_M(STG, 0, EOS, CONS, LAY, MATH), ARMON_FAST_ROW_M(STG, 1, EOS, CONS, LAY, MATH), \
-            ARMON_FAST_ROW_M(STG, 2, EOS, CONS, LAY, MATH), ARMON_FAST_ROW_M(STG, 3, EOS, CONS, LAY, MATH), \
+            ARMON_FAST_ROW_M(STG, 0, EOS, CONS, LAY, MATH, DXP), ARMON_FAST_ROW_M(STG, 1, EOS, CONS, LAY, MATH, DXP), \
+            ARMON_FAST_ROW_M(STG, 2, EOS, CONS, LAY, MATH, DXP), ARMON_FAST_ROW_M(STG, 3, EOS, CONS, LAY, MATH, DXP), \
         };                                                                                  \
         if (rl < 0 || rl > 3 || proj < 0 || proj > 1 || tr < 0 || tr > 1) return nullptr;   \
         return table[rl][proj][tr];                                                         \
     }
-#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS, LAY) ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH_FAST)
+#define ARMON_DEFINE_FAST_TABLE(NAME, STG, EOS, CONS, LAY) ARMON_DEFINE_FAST_TABLE_M(NAME, STG, EOS, CONS, LAY, MATH_FAST, 0)

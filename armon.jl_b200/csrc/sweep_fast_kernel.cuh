@@ -424,7 +424,7 @@ struct PipeS {
     sd S2b, S2r;                                            // 2 dxl of cell a-7 and its refined reciprocal
 };
 
-template <int RL, int PROJ, int EOS, int J, int TR, int EMIT>
+template <int RL, int PROJ, int EOS, int J, int TR, int EMIT, int DXP>
 __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, PipeS &P, const FastIter &I, const sd dt,
                                             const typename Div<sd, DIV_FLAGGED>::Rcp &inv_dx, const bool ok)
 {
@@ -538,7 +538,7 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
         R t_ru = dXr * P.Lu[Z3] - (Anru - P.Aru);
         R t_rt = dXr * P.Lt[Z3] - (Anrt - P.Art);
         R t_rE = dXr * P.LE[Z3] - (AnrE - P.ArE);
-        if (A.dx_pow2) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two
+        if (DXP) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two (compile-time: no branch in the step)
             const R idx(A.inv_dx);
             t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
         } else {
@@ -786,7 +786,8 @@ __device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
 // sweep of a cycle): per thread in march order, per warp by a fixed butterfly, one partial per warp for k_diag_final.
 // MATH = MATH_STRICT: the reference's operation order with correctly rounded divisions (strict_step, section 6.) and the
 // chunk-granular hand-over of out-of-range operands to sweep_fixup_kernel (chunk_end, sweep_async_kernel.cuh).
-template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS, int MATH = MATH_FAST>
+// DXP (strict arithmetic only): 1 = the cell size is a power of two, the host checked it (SweepArgs::dx_pow2).
+template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS, int MATH = MATH_FAST, int DXP = 0>
 __global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
 sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 {
@@ -941,7 +942,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     ChunkFix C;
     C.tot_a = 0ULL; C.tot_t = 0ULL; C.taint = 0; C.always = false;
     if (MATH == MATH_STRICT) {
-        inv_dx = Div<sd, DIV_FLAGGED>::prepare(sd(A.dx), T.flag);
+        if (!DXP) inv_dx = Div<sd, DIV_FLAGGED>::prepare(sd(A.dx), T.flag);
         range_check_dividend(dt, T.flag);
         C.always = T.flag.bad();
     }
@@ -956,7 +957,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
 #define FK_STEP(Jv, EMITv, OK)                                                                              \
-    if constexpr (MATH == MATH_STRICT) strict_step<RL, PROJ, EOS, Jv, TR, EMITv>(A, T, P, I, sd(dt), inv_dx, OK);  \
+    if constexpr (MATH == MATH_STRICT) strict_step<RL, PROJ, EOS, Jv, TR, EMITv, DXP>(A, T, P, I, sd(dt), inv_dx, OK);  \
     else fast_step<RL, PROJ, EOS, Jv, TR, EMITv, CONS, LAY>(A, T, P, I, dt, OK);
 #define FK_BEGIN(it)                                                                                        \
     {                                                                                                       \

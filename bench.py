@@ -301,10 +301,9 @@ class GpuJob:
         avg_s = run["sweep_ms"] / max(run["sweep_n"], 1) / 1e3
         achieved = BYTES_PER_CELL_SWEEP * self.local_cells / avg_s / 1e9
         biz = self.w["test"] == "Bizarrium"
-        variant = os.environ.get("ARMON_B200_KERNEL") or {"fast": "tma", "strict": "async", "ieee": "single"}[self.math]
+        variant = os.environ.get("ARMON_B200_KERNEL") or {"fast": "tma", "strict": "single", "ieee": "single"}[self.math]
         kname = {"tma": "sweep_fast_kernel<STG_TMA", "async2": "sweep_fast_kernel<STG_CPA16",
-                 "async": "sweep_async_kernel<sd, DIV_FLAGGED",
-                 "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}[variant]
+                 "single": "sweep_kernel<%s" % {"fast": "fd, DIV_FAST", "strict": "sd, DIV_FLAGGED", "ieee": "sd, DIV_IEEE"}[self.math]}.get(variant, variant)
         # which layout the fused path actually ran in (sweep_fast_kernel.cuh 5.): asked from the library, not assumed
         if self.grid.fused_layout_is_tiled() == 1:
             variant, kname = "tiled", "sweep_fast_kernel<STG_TMA, LAY_TILED"

@@ -67,11 +67,12 @@ enum { ARMON_MATH_STRICT = 0,   /* IEEE operation order of the reference source,
        ARMON_MATH_IEEE = 2 };   /* as STRICT but with nvcc's full IEEE division/sqrt (slow paths for every operand) */
 
 /* marching kernel of the fused sweep.  AUTO: TMA for math_mode fast, ASYNC for strict, SINGLE for ieee (and for
- * strict when the input pitch is odd: its 16-byte staging copies need an even pitch; the fast kernels fall back to
- * 8-byte staging copies by themselves). */
+ * strict when the input pitch is odd: the tensor maps of its TMA staging need 16-byte aligned rows; the fast kernels
+ * fall back to 8-byte staging copies by themselves). */
 enum { ARMON_KERNEL_AUTO = 0,
        ARMON_KERNEL_SINGLE = 1,     /* register prefetch, no shared-memory staging (any math mode) */
-       ARMON_KERNEL_ASYNC = 4,      /* strict: inputs staged through shared memory with cp.async + IEEE fix-up kernel */
+       ARMON_KERNEL_ASYNC = 4,      /* strict: the strict arithmetic on the fast kernel's four-chain schedule (TMA staging)
+                                       + IEEE fix-up kernel; the name is the ABI's from round 1 (cp.async staging) */
        ARMON_KERNEL_ASYNC2 = 5,     /* fast: explicit-arithmetic software-pipelined kernel, cp.async (16-byte) staging */
        ARMON_KERNEL_TMA = 6         /* fast: the same kernel staged by the TMA (cp.async.bulk.tensor.2d + mbarrier) */ };
 
@@ -277,8 +278,9 @@ int armon_solver_sweep_launches(armon_solver *solver, uint64_t *count);
 int armon_solver_tiled(armon_solver *solver, int32_t *tiled);
 /* Kernel of the bit-exact arithmetic mode (no reference counterpart): *chains = 1 when the solver's strict sweeps run
  * on the four-chain schedule of the fast kernel (sweep_fast_kernel<..., MATH_STRICT>, TMA staging; the default for
- * math_mode strict, ARMON_B200_STRICT=async turns it off), 0 when they run the unskewed cp.async kernel or the solver
- * is not in strict mode.  Same bits either way; informational (bench.py names the kernel it timed). */
+ * math_mode strict -- sweeps whose rows are not 16-byte aligned still take the register-prefetch kernel), 0 when they
+ * all run the register-prefetch kernel (kernel_variant single, ARMON_B200_STRICT=single) or the solver is not in strict
+ * mode.  Same bits either way; informational (bench.py names the kernel it timed). */
 int armon_solver_strict_chains(armon_solver *solver, int32_t *chains);
 
 /* Per-cycle diagnostics without a host round trip: the reference's `silent <= 1` log line (src/solver.jl:359-371:

@@ -289,7 +289,7 @@ function fused_layout_is_tiled(params::ArmonParameters{<:Any, <:B200Device}, gri
 end
 
 # Kernel of the bit-exact mode (armon_solver_strict_chains): 1 = strict arithmetic on the fast kernel's four-chain
-# schedule (default for math_mode strict), 0 = unskewed cp.async kernel (ENV["ARMON_B200_STRICT"] = "async") or another mode.
+# schedule (default for math_mode strict), 0 = register-prefetch kernel (ENV["ARMON_B200_STRICT"] = "single") or another mode.
 function strict_kernel_is_chains(params::ArmonParameters{<:Any, <:B200Device}, grid::BlockGrid)
     chains = Ref{Int32}(0)
     @b200call(:armon_solver_strict_chains, (Ptr{Cvoid}, Ptr{Int32}), fused_solver(params, grid), chains)

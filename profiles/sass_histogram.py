@@ -57,10 +57,9 @@ PRODUCT = {
     "tiled_fast_biz": ("sweep_fast_inst_tiled_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1ELi0ELi1E"),
     "async2_fast_pg": ("sweep_fast_inst_cpa16_pg.o", "sweep_fast_kernelILi1ELi2ELi1ELi0ELi1E"),
     "async2_fast_biz": ("sweep_fast_inst_cpa16_biz.o", "sweep_fast_kernelILi1ELi2ELi1ELi1ELi1E"),
-    "chains_strict_pg": ("sweep_fast_inst_strict_pg.o", "sweep_fast_kernelILi0ELi2ELi1ELi0ELi1E"),
-    "chains_strict_biz": ("sweep_fast_inst_strict_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1E"),
-    "async_strict_pg": ("sweep_async_inst_strict_pg.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi0ELi1E"),
-    "async_strict_biz": ("sweep_async_inst_strict_biz.o", "sweep_async_kernelI2sdLi1ELi2ELi1ELi1ELi1E"),
+    # strict arithmetic on the four-chain schedule; the benched grids have power-of-two cell sizes (the _dxp instantiations)
+    "chains_strict_pg": ("sweep_fast_inst_strict_dxp_pg.o", "sweep_fast_kernelILi0ELi2ELi1ELi0ELi1E"),
+    "chains_strict_biz": ("sweep_fast_inst_strict_dxp_biz.o", "sweep_fast_kernelILi0ELi2ELi1ELi1ELi1E"),
 }
 
 

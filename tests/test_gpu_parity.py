@@ -427,7 +427,7 @@ def test_strict_mode_handles_tiny_operands_like_ieee():
     g_strict, g_async, g_ieee = run("strict"), run("strict", "async"), run("ieee")
     for var in ("rho", "u", "v", "E"):
         assert_same(g_strict.real(var), g_ieee.real(var), var)
-        assert_same(g_async.real(var), g_ieee.real(var), var + " (cp.async kernel + fix-up kernel)")
+        assert_same(g_async.real(var), g_ieee.real(var), var + " (four-chain strict kernel + fix-up kernel)")
     assert g_strict.time_state().current_dt == g_ieee.time_state().current_dt == g_async.time_state().current_dt
     g_strict.close(); g_async.close(); g_ieee.close()
 

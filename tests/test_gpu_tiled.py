@@ -158,7 +158,7 @@ def test_tiled_layout_cycles_past_the_end_and_graph_replay():
 
 
 def run_strict(params, kernel):
-    """armon(params) in math_mode strict with the sweep kernel forced (ARMON_B200_STRICT = chains | async)."""
+    """armon(params) in math_mode strict with the sweep kernel forced (ARMON_B200_STRICT = chains | single)."""
     old = os.environ.get("ARMON_B200_STRICT")
     os.environ["ARMON_B200_STRICT"] = kernel
     try:
@@ -179,16 +179,16 @@ def run_strict(params, kernel):
 @pytest.mark.parametrize("test,N,scheme,limiter,projection,splitting,cycles,segment", CASES)
 def test_strict_chains_kernel_gives_the_same_bits(test, N, scheme, limiter, projection, splitting, cycles, segment):
     """The two kernels of the bit-exact mode -- the strict arithmetic on the four-chain schedule of the fast kernel
-    (sweep_fast_kernel<..., MATH_STRICT>, the default) and the unskewed cp.async kernel -- and the strict CPU oracle
-    agree bit for bit: every test case, scheme, limiter, projection and splitting, forced march segments, extents from
+    (sweep_fast_kernel<..., MATH_STRICT>, the default) and the register-prefetch kernel (one chain per step, what rows
+    that are not 16-byte aligned still take) -- and the strict CPU oracle agree bit for bit: every test case, scheme, limiter, projection and splitting, forced march segments, extents from
     one band of rows to 1024 x 520 (non-power-of-two cell sizes included: the x / dx division path)."""
     kw = dict(N=N, maxcycle=cycles, scheme=scheme, riemann_limiter=limiter, projection=projection,
               axis_splitting=splitting, march_segment=segment, math_mode="strict")
     s_c, chains = run_strict(reference_params(test, **kw), "chains")
-    s_a, unskewed = run_strict(reference_params(test, **kw), "async")
+    s_a, unskewed = run_strict(reference_params(test, **kw), "single")
     assert (s_c.cycles, s_c.last_dt, s_c.final_time) == (s_a.cycles, s_a.last_dt, s_a.final_time)
     for v in VARS:
-        assert_same(chains[v], unskewed[v], f"{test} {N} {v}: chains vs async")
+        assert_same(chains[v], unskewed[v], f"{test} {N} {v}: chains vs single")
     okw = {k: v for k, v in kw.items() if k not in ("march_segment", "math_mode")}
     orc = OracleSolver(reference_params(test, **okw), "strict", nthreads=os.cpu_count() or 1)
     _, dt, ncyc, err = orc.time_loop()
