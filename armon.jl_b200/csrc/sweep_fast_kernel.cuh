@@ -81,6 +81,12 @@ constexpr int FK_CS = 8;                       // sound-speed ring slots (writte
 constexpr int FK_PITCH = FK_K + 2;             // staging tile row pitch: rows stay 16-byte aligned, 2-way write conflicts
 static_assert(FK_K == 8 || FK_K == 16, "transposed staging chunk");
 
+// Ring slot and mbarrier phase of staging group G.  Fast arithmetic: the 4 groups of the ring.  Strict arithmetic: 3 groups
+// (the previous one, kept for the re-reads of chain C, the current one and one in flight -- at its pace 4 to 8 rows in
+// flight cover the memory latency several times); the fourth group's 4 KB hold the Lagrangian rings (strict_step).
+template <int MATH> __device__ __forceinline__ int fk_slot(int G) { return MATH == 1 ? G % 3 : G & (4 - 1); }
+template <int MATH> __device__ __forceinline__ unsigned fk_phase(int G) { return (unsigned)((MATH == 1 ? G / 3 : G >> 2) & 1); }
+
 struct FastWarpShared {
     double ring[FK_NG][4][FK_GROUP][32];                   // [group][variable][row in group][lane]
     double cring[FK_CS][32];
@@ -225,6 +231,7 @@ struct FastIter {
     unsigned row_mask;           // strict arithmetic: bit J set <=> row J of the current group exists in the array (the others
                                  // were zero-filled by the copy engine and are given a benign state before use)
     const double *gbm;           // strict_step: this lane's column of the ring group holding rows a-4-J .. (the previous group)
+    volatile double *lr;         // strict_step: this lane's column of the Lagrangian rings [rho, ua, ut, E][slot] (fourth ring group)
 };
 
 __device__ __forceinline__ void fk_store4_if(bool ok, double *p, double a, double b, double c, double d);
@@ -417,8 +424,8 @@ struct PipeS {
     sd Gu[4], Gp[4];                                        // Godunov states of interfaces a-1 .. a-3
     sd Fu[4], Fp[4], FpFu[4];                               // flux used (GAD or Godunov) of interfaces a-3, a-4, and p u
     sd disp[4], dxl[4];                                     // interfaces / cells a-5 .. a-7: dt Fu, Lagrangian width
-    sd Lr[4], Lu[4], Lt[4], LE[4];                          // Lagrangian cells a-5 .. a-7: rho, ua, ut, E (the products
-                                                            // rho {ua, ut, E} are formed where they are used: same bits)
+    // (the Lagrangian cells a-5 .. a-7 -- rho, ua, ut, E -- live in shared-memory rings, FastIter::lr: 24 registers less;
+    // the products rho {ua, ut, E} are formed where they are used: same operands, same bits)
     sd Ar, Aru, Art, ArE;                                   // advection flux of interface a-7
     sd Sr, Sru, Srt, SrE;                                   // limited slopes of cell a-7
     sd S2b, S2r;                                            // 2 dxl of cell a-7 and its refined reciprocal
@@ -497,34 +504,38 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
     R sr(0.), sru(0.), srt(0.), srE(0.);
     typename D::Rcp k2;
     k2.b = 2.0; k2.r = 0.5;
+    // Lagrangian cells from the shared rings [variable][slot]; cell a-7 also serves the projection below
+#define LRING(var, Z) I.lr[((var) * 4 + (Z)) * 32]
+    const R Lr3(LRING(0, Z3)), Lu3(LRING(1, Z3)), Lt3(LRING(2, Z3)), LE3(LRING(3, Z3));
     {
         const R d = P.disp[Z2];
         const unsigned long long pm = d.v > 0.0 ? ~0ULL : 0ULL;   // disp > 0: the upwind cell is a-7
-        // rho {ua, ut, E} of the Lagrangian cells a-7, a-6 (cell_update!'s products, formed here: same operands, same bits)
-        const R Lru3 = P.Lr[Z3] * P.Lu[Z3], Lrt3 = P.Lr[Z3] * P.Lt[Z3], LrE3 = P.Lr[Z3] * P.LE[Z3];
-        const R Lru2 = P.Lr[Z2] * P.Lu[Z2], Lrt2 = P.Lr[Z2] * P.Lt[Z2], LrE2 = P.Lr[Z2] * P.LE[Z2];
+        const R Lr2(LRING(0, Z2)), Lr1(LRING(0, Z1));
+        // rho {ua, ut, E} (cell_update!'s products, formed here: same operands, same bits)
+        const R Lru3 = Lr3 * Lu3, Lrt3 = Lr3 * Lt3, LrE3 = Lr3 * LE3;
+        const R Lru2 = Lr2 * R(LRING(1, Z2)), Lrt2 = Lr2 * R(LRING(2, Z2)), LrE2 = Lr2 * R(LRING(3, Z2));
         if (PROJ == ARMON_PROJ_EULER_2ND) {
             const R dxl_m = P.dxl[Z3], dxl_0 = P.dxl[Z2], dxl_p = P.dxl[Z1];
             const R two_dxl = R(2.) * dxl_0;
             const R r_m = D::div_pos(two_dxl, dxl_0 + dxl_m, f);
             const R r_p = D::div_pos(two_dxl, dxl_0 + dxl_p, f);
             k2 = D::prepare_pos(two_dxl, f);
-            sr = slope_minmod_fused<R>(P.Lr[Z3], P.Lr[Z2], P.Lr[Z1], r_m, r_p);
-            sru = slope_minmod_fused<R>(Lru3, Lru2, P.Lr[Z1] * P.Lu[Z1], r_m, r_p);
-            srt = slope_minmod_fused<R>(Lrt3, Lrt2, P.Lr[Z1] * P.Lt[Z1], r_m, r_p);
-            srE = slope_minmod_fused<R>(LrE3, LrE2, P.Lr[Z1] * P.LE[Z1], r_m, r_p);
+            sr = slope_minmod_fused<R>(Lr3, Lr2, Lr1, r_m, r_p);
+            sru = slope_minmod_fused<R>(Lru3, Lru2, Lr1 * R(LRING(1, Z1)), r_m, r_p);
+            srt = slope_minmod_fused<R>(Lrt3, Lrt2, Lr1 * R(LRING(2, Z1)), r_m, r_p);
+            srE = slope_minmod_fused<R>(LrE3, LrE2, Lr1 * R(LRING(3, Z1)), r_m, r_p);
 
             const R dxe = sblend(pm, -(dx - P.disp[Z3]), dx + P.disp[Z1]);
             typename D::Rcp ksel;
             ksel.b = sblend(pm, P.S2b, R(k2.b)).v;
             ksel.r = sblend(pm, P.S2r, R(k2.r)).v;
             const R lf = D::quot(dxe, ksel, f);
-            Anr = d * (sblend(pm, P.Lr[Z3], P.Lr[Z2]) - sblend(pm, P.Sr, sr) * lf);
+            Anr = d * (sblend(pm, Lr3, Lr2) - sblend(pm, P.Sr, sr) * lf);
             Anru = d * (sblend(pm, Lru3, Lru2) - sblend(pm, P.Sru, sru) * lf);
             Anrt = d * (sblend(pm, Lrt3, Lrt2) - sblend(pm, P.Srt, srt) * lf);
             AnrE = d * (sblend(pm, LrE3, LrE2) - sblend(pm, P.SrE, srE) * lf);
         } else {
-            Anr = d * sblend(pm, P.Lr[Z3], P.Lr[Z2]);
+            Anr = d * sblend(pm, Lr3, Lr2);
             Anru = d * sblend(pm, Lru3, Lru2);
             Anrt = d * sblend(pm, Lrt3, Lrt2);
             AnrE = d * sblend(pm, LrE3, LrE2);
@@ -533,11 +544,11 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
 
     // ---- chain E (continues D), projection of cell k = a-7 (src/projection_schemes.jl:23-41) ----
     if (EMIT == 1) {
-        const R dXr = P.dxl[Z3] * P.Lr[Z3];
+        const R dXr = P.dxl[Z3] * Lr3;
         R t_r = dXr - (Anr - P.Ar);
-        R t_ru = dXr * P.Lu[Z3] - (Anru - P.Aru);
-        R t_rt = dXr * P.Lt[Z3] - (Anrt - P.Art);
-        R t_rE = dXr * P.LE[Z3] - (AnrE - P.ArE);
+        R t_ru = dXr * Lu3 - (Anru - P.Aru);
+        R t_rt = dXr * Lt3 - (Anrt - P.Art);
+        R t_rE = dXr * LE3 - (AnrE - P.ArE);
         if (DXP) {   // x / dx == x * (1/dx) bit for bit when dx is a power of two (compile-time: no branch in the step)
             const R idx(A.inv_dx);
             t_r = t_r * idx; t_ru = t_ru * idx; t_rt = t_rt * idx; t_rE = t_rE * idx;
@@ -580,7 +591,8 @@ __device__ __forceinline__ void strict_step(const SweepArgs &A, SweepThread &T, 
     P.Gu[Z0] = A_Gu; P.Gp[Z0] = A_Gp;
     P.Fu[Z2] = B_Fu; P.Fp[Z2] = B_Fp; P.FpFu[Z2] = B_FpFu;
     P.disp[Z0] = C_disp; P.dxl[Z0] = C_dxl;
-    P.Lr[Z0] = C_Lr; P.Lu[Z0] = C_Lu; P.Lt[Z0] = C_Lt; P.LE[Z0] = C_LE;
+    LRING(0, Z0) = C_Lr.v; LRING(1, Z0) = C_Lu.v; LRING(2, Z0) = C_Lt.v; LRING(3, Z0) = C_LE.v;
+#undef LRING
 #undef ZS
 }
 
@@ -610,7 +622,7 @@ __device__ __forceinline__ void fk_pipe_init(PipeS &P)
     for (int j = 0; j < 4; j++) {
         P.cp[j] = R(1.); P.crc[j] = R(1.);
         P.Gu[j] = R(0.); P.Gp[j] = R(1.); P.Fu[j] = R(0.); P.Fp[j] = R(1.); P.FpFu[j] = R(0.); P.disp[j] = R(0.);
-        P.dxl[j] = R(1.); P.Lr[j] = R(1.); P.Lu[j] = R(0.); P.Lt[j] = R(0.); P.LE[j] = R(1.);
+        P.dxl[j] = R(1.);   // (Lagrangian rings: rho = E = 1, ua = ut = 0 from the initial fill of the staging ring)
     }
     P.Ar = R(0.); P.Aru = R(0.); P.Art = R(0.); P.ArE = R(0.);
     P.Sr = R(0.); P.Sru = R(0.); P.Srt = R(0.); P.SrE = R(0.); P.S2b = R(2.); P.S2r = R(0.5);
@@ -893,8 +905,8 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
         // never start a copy that the warp will not wait for: it could land after the CTA has exited
         if (STG == STG_TMA) {
             if (G < n_groups && fk_elect_one()) {
-                const unsigned bar = bar_u32 + 8u * (unsigned)(G & (FK_NG - 1));
-                const unsigned dst = ring_u32 + (unsigned)(G & (FK_NG - 1)) * (FK_GS * 8u);
+                const unsigned bar = bar_u32 + 8u * (unsigned)fk_slot<MATH>(G);
+                const unsigned dst = ring_u32 + (unsigned)fk_slot<MATH>(G) * (FK_GS * 8u);
                 fk_mbar_expect_tx(bar, 4u * FK_VS * 8u);
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
@@ -926,13 +938,13 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
             async_commit();
         }
     };
-    // strict arithmetic: the group consumed by the previous iteration stays in the ring (chain C re-reads ut and E of cell
-    // a-4 from it instead of carrying them in registers), so 8 rows are in flight instead of 12
-    constexpr int LEAD = MATH == MATH_STRICT ? FK_NG - 1 : FK_NG;
+    // strict arithmetic: three staging groups, of which the one consumed by the previous iteration stays in the ring (the
+    // chains re-read the inputs of the cells a-1 .. a-4 from it instead of carrying them in registers): groups it and
+    // it + 1 are issued ahead
+    constexpr int LEAD = MATH == MATH_STRICT ? 2 : FK_NG;
     issue_group(0);
     issue_group(1);
-    issue_group(2);
-    if (LEAD == FK_NG) issue_group(3);
+    if (LEAD == FK_NG) { issue_group(2); issue_group(3); }
 
     typename std::conditional<MATH == MATH_STRICT, PipeS, PipeF>::type P;
     fk_pipe_init(P);
@@ -954,6 +966,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     const long long q_lane = (((w0 + A.g) >> 2) + (lane >> 2)) * (4 * A.pitch_out) + (lane & 3) * 8;
     FastIter I;
     I.q_off = 0; I.qok = false; I.row_mask = 0xfu;
+    I.lr = const_cast<double *>(ring) + (FK_NG - 1) * FK_GS;
 
     // Iteration `it` = steps 4 it .. 4 it + 3 (J = 0 .. 3).
 #define FK_STEP(Jv, EMITv, OK)                                                                              \
@@ -962,8 +975,8 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
 #define FK_BEGIN(it)                                                                                        \
     {                                                                                                       \
         const int p_ = (it) & 1;                                                                            \
-        I.gb0 = ring + ((it) & (FK_NG - 1)) * FK_GS;                                                        \
-        I.gbm = ring + (((it) + FK_NG - 1) & (FK_NG - 1)) * FK_GS;                                          \
+        I.gb0 = ring + fk_slot<MATH>(it) * FK_GS;                                                           \
+        I.gbm = ring + fk_slot<MATH>((it) + (MATH == MATH_STRICT ? 2 : 3)) * FK_GS;   /* group it - 1 */    \
         I.cw = cring + p_ * 4 * 32;                                                                         \
         I.cr = cring + (p_ ^ 1) * 4 * 32;                                                                   \
         if (MATH == MATH_STRICT) {   /* rows a_begin + 4 it + J inside [-g, nm + g): bits J of the mask */          \
@@ -973,7 +986,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
             I.row_mask = m_hi_ & m_lo_;                                                                     \
         }                                                                                                   \
         if (STG == STG_TMA) {                                                                               \
-            if (!landed) fk_mbar_wait(bar_u32 + 8u * (unsigned)((it) & (FK_NG - 1)), (unsigned)(((it) >> 2) & 1)); \
+            if (!landed) fk_mbar_wait(bar_u32 + 8u * (unsigned)fk_slot<MATH>(it), fk_phase<MATH>(it));      \
         } else { async_wait<3>(); __syncwarp(); }                                                           \
         if (MATH == MATH_STRICT && I.row_mask != 0xfu) {                                                    \
             /* rows outside the array were zero-filled by the copy engine: give them a benign state (rho = 1e4, */ \
@@ -988,7 +1001,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     }
     /* early look at the barrier of the next iteration's group */
 #define FK_PEEK(it)                                                                                         \
-    if (STG == STG_TMA) landed = fk_mbar_test(bar_u32 + 8u * (unsigned)(((it) + 1) & (FK_NG - 1)), (unsigned)((((it) + 1) >> 2) & 1));
+    if (STG == STG_TMA) landed = fk_mbar_test(bar_u32 + 8u * (unsigned)fk_slot<MATH>((it) + 1), fk_phase<MATH>((it) + 1));
 #define FK_END(it)                                                                                          \
     {                                                                                                       \
         __syncwarp();   /* every lane has read the last row of group it: refill its slot */                 \
