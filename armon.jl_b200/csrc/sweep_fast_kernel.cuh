@@ -53,6 +53,13 @@
 //    output side; the 4 ghost columns this brings into the first warp are masked like the ragged tail.  The arithmetic
 //    is untouched: results are bit-identical to the row-major path.  The ghost rows of a side are exactly one band, so
 //    the boundary-condition fill only changes its indexing and the halo copies (NCCL, local blocks) do not change at all.
+//
+// 6. THE BIT-EXACT MODE ON THE SAME SKELETON (MATH_STRICT; details above strict_step).  math_mode strict -- the reference's
+//    operation order, no contraction, correctly rounded branch-free divisions, bit-identical to the CPU oracle -- runs
+//    this kernel's staging and four-chain schedule with its own step function; row-major layouts, because the IEEE fix-up
+//    of out-of-range division operands (sweep_fixup_kernel.cuh) works on them.  Three staging groups instead of four: the
+//    fourth group's shared memory holds the Lagrangian rings, which is what leaves ptxas the registers to interleave the
+//    chains (0.345 -> 0.417 of the copy bandwidth at 16384^2 against the one-chain kernel of round 1).
 #pragma once
 
 #include <cuda.h>
