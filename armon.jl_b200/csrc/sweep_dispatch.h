@@ -8,7 +8,7 @@
 #pragma once
 #include "sweep_kernel.cuh"
 #include "sweep_fixup_kernel.cuh"
-#include "sweep_async_kernel.cuh"
+#include "sweep_staged_common.cuh"
 
 typedef void (*sweep_fn_t)(const SweepArgs);
 typedef void (*sweep_fixup_fn_t)(const SweepArgs, const FixupArgs);

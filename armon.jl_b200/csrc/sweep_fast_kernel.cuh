@@ -1,6 +1,6 @@
 // sweep_fast_kernel.cuh -- the fast-mode marching kernel (math_mode fast: the product's default and the benched path).
 //
-// Same sweep, data layout and HBM traffic as sweep_kernel.cuh / sweep_async_kernel.cuh (read those first: thread <->
+// Same sweep, data layout and HBM traffic as sweep_kernel.cuh (read it first; sweep_staged_common.cuh has the helpers: thread <->
 // column, march along the strided axis, rolling register window, inputs staged through a per-warp shared-memory
 // ring).  What is specific to this file:
 //
@@ -66,7 +66,7 @@
 
 #include <type_traits>
 
-#include "sweep_async_kernel.cuh"
+#include "sweep_staged_common.cuh"
 
 enum { STG_TMA = 0, STG_CPA16 = 1, STG_CPA8 = 2 };
 enum { LAY_ROWS = 0, LAY_TILED = 1 };          // layout of the input AND of the output of a sweep
@@ -804,7 +804,7 @@ __device__ __forceinline__ void async_copy8(unsigned dst, const double *src)
 // CONS = 1: also accumulates the conservation sums of the cells it stores (per-cycle diagnostics fused into the last
 // sweep of a cycle): per thread in march order, per warp by a fixed butterfly, one partial per warp for k_diag_final.
 // MATH = MATH_STRICT: the reference's operation order with correctly rounded divisions (strict_step, section 6.) and the
-// chunk-granular hand-over of out-of-range operands to sweep_fixup_kernel (chunk_end, sweep_async_kernel.cuh).
+// chunk-granular hand-over of out-of-range operands to sweep_fixup_kernel (chunk_end, sweep_staged_common.cuh).
 // DXP (strict arithmetic only): 1 = the cell size is a power of two, the host checked it (SweepArgs::dx_pow2).
 template <int STG, int RL, int PROJ, int EOS, int TR, int CONS = 0, int LAY = LAY_ROWS, int MATH = MATH_FAST, int DXP = 0>
 __global__ void __launch_bounds__(ASYNC_TPB, FAST_MIN_BLOCKS)
@@ -880,7 +880,7 @@ sweep_fast_kernel(const SweepArgs A, const __grid_constant__ SweepTmaMaps M)
     const unsigned ring_u32 = fk_smem_u32(&S.ring[0][0][0][0]);
     const unsigned bar_u32 = fk_smem_u32(&S.full[0]);
     const int col0 = (int)(w0 + A.g), row0_arr = (int)(a_begin + A.g);
-    AsyncLane L;   // cp.async variants: per-thread copy plan (see sweep_async_kernel.cuh)
+    AsyncLane L;   // cp.async variants: per-thread copy plan (see sweep_staged_common.cuh)
     L.active = false;
     if (STG == STG_TMA) {
         if (lane == 0) {

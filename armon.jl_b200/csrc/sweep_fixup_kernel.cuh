@@ -2,7 +2,7 @@
 //
 // The strict mode of the cp.async-staged kernels divides with a branch-free correctly rounded sequence that is only
 // proven for operands inside a range (common.cuh).  A thread that meets an operand outside it appends
-// (first row << 32 | column) to a work list (chunk_end, sweep_async_kernel.cuh); this kernel recomputes `fix_rows`
+// (first row << 32 | column) to a work list (chunk_end, sweep_staged_common.cuh); this kernel recomputes `fix_rows`
 // rows of each listed column with nvcc's full IEEE division (march_segment<DIV_IEEE>, direct stores), one thread per
 // entry, so that the strict mode is bit-identical to IEEE for every operand.
 #pragma once

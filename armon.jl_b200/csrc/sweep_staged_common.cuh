@@ -1,4 +1,4 @@
-// sweep_async_kernel.cuh -- shared pieces of the shared-memory staged marching kernels (sweep_fast_kernel.cuh): the CTA
+// sweep_staged_common.cuh -- shared pieces of the shared-memory staged marching kernels (sweep_fast_kernel.cuh): the CTA
 // size, the per-thread cp.async copy helpers of the staging variants for rows that are not 16-byte aligned
 // (STG_CPA16 / STG_CPA8), and the chunk-granular range bookkeeping of the strict (bit-exact) arithmetic.
 //
